@@ -1,0 +1,141 @@
+/*
+ * nr_b200.h -- C ABI of the B200-native differentiable mesh rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of hiroharu-kato/neural_renderer:
+ * the `Rasterize` function object (neural_renderer/rasterize.py:19-897) and the
+ * post-processing owned by `rasterize_rgbad` (rasterize.py:945-969).  The
+ * reference has no FFI of its own -- CuPy hands raw device pointers to
+ * JIT-compiled kernels (`chainer.cuda.elementwise(...)(arrays)`,
+ * rasterize.py:236, :277, :359, :435, :745, :789, :844) -- so the entry points
+ * below are what a binding for that path would call instead:
+ *
+ *   nr_b200_forward    replaces Rasterize.forward_gpu   (rasterize.py:467-513: K1 :242, K2 :281, K4 :372,
+ *                      alpha/background :440-465) fused with the transpose / vertical flip / 2x2 average
+ *                      pooling of rasterize_rgbad (rasterize.py:953-969)
+ *   nr_b200_backward   replaces Rasterize.backward_gpu  (rasterize.py:849-889: K5 :528, K6 :760, K7 :805)
+ *                      fused with the backward of that same post-processing
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every pointer is a DEVICE pointer owned by the caller (torch allocator,
+ *     cudaMalloc, ...) unless it says "host"; the stream is a cudaStream_t passed as void*; launches are
+ *     asynchronous on that stream; nothing is allocated behind the caller's back (scratch = explicit workspace);
+ *   - return value 0 = NR_OK, negative = error (nr_b200_error_string); never throws, no global state, re-entrant;
+ *   - all images are planar, row-major, in IMAGE orientation: row 0 is the TOP row (the reference's
+ *     `[:, ::-1, :]` flip is folded in), i.e. raster row yi (NDC y up) is stored at row S-1-yi;
+ *   - S = raster size = image_size, or 2*image_size with NR_ANTI_ALIASING (then the API images are the 2x2
+ *     means, size S/2, and the raster-resolution maps are still written because the backward needs them);
+ *   - float32 / int32 throughout, C-contiguous.
+ */
+#ifndef NR_B200_H_
+#define NR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NR_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NR_B200_API __attribute__((visibility("default")))
+#else
+#define NR_B200_API
+#endif
+
+/* error codes */
+#define NR_OK 0
+#define NR_ERR_INVALID_ARG (-1)
+#define NR_ERR_WORKSPACE (-2)
+#define NR_ERR_CUDA (-3)
+#define NR_ERR_UNSUPPORTED (-4)
+
+/* flags */
+#define NR_RETURN_RGB 1u      /* Rasterize(return_rgb=True): needs textures                                   */
+#define NR_RETURN_ALPHA 2u    /* Rasterize(return_alpha=True)                                                   */
+#define NR_RETURN_DEPTH 4u    /* Rasterize(return_depth=True)                                                   */
+#define NR_ANTI_ALIASING 8u   /* rasterize_rgbad(anti_aliasing=True): raster_size = 2 * image_size            */
+#define NR_BG_PER_BATCH 16u   /* background_color given as [B,3] (rasterize.py:464-465) in `background_batch`  */
+#define NR_TEX_Z_BATCH0 32u   /* reproduce rasterize.py:389: the texture sampler reads vertex depths of batch  */
+                              /* item 0 (reference-exact; clear it for per-item depths)                        */
+#define NR_GRAD_ACCUMULATE 64u /* backward: add into grad_faces / grad_textures instead of zero-filling first */
+
+typedef struct nr_b200_forward_args {
+    uint32_t struct_size; /* sizeof(nr_b200_forward_args), for ABI evolution */
+    uint32_t flags;
+    int32_t batch_size;   /* B */
+    int32_t num_faces;    /* F */
+    int32_t raster_size;  /* S (already doubled when NR_ANTI_ALIASING) */
+    int32_t texture_size; /* ts (>= 2) when NR_RETURN_RGB, else ignored */
+    double near_;         /* reject zp <= near   (compared in double, like the pasted literal, rasterize.py:331) */
+    double far_;          /* reject far <= zp; uncovered depth = (float)far (rasterize.py:296, :480)             */
+    double eps;           /* texture-coordinate clamp `ts - 1 - eps` (rasterize.py:402)                          */
+    float background[3];  /* uniform background colour (host values)                                             */
+    float _pad0;
+    const float *faces;            /* [B,F,3,3]  x,y in NDC [-1,1], z = camera depth                            */
+    const float *textures;         /* [B,F,ts,ts,ts,3] or NULL                                                  */
+    const float *background_batch; /* [B,3] device, only with NR_BG_PER_BATCH                                   */
+    /* raster-resolution maps, saved for the backward pass (all required unless noted) */
+    int32_t *face_index_map; /* [B,S,S]   -1 where empty                                                      */
+    float *weight_map;       /* [B,3,S,S] barycentric weights of the winning face, 0 where empty              */
+    float *depth_map;        /* [B,S,S]   zp, (float)far where empty; IS the depth image when !ANTI_ALIASING  */
+    float *rgb_map;          /* [B,3,S,S] post-background colour; required with NR_RETURN_RGB; IS the rgb     */
+                             /*           image when !ANTI_ALIASING                                           */
+    float *alpha_map;        /* [B,S,S]   0/1; optional (NULL ok); IS the alpha image when !ANTI_ALIASING     */
+    /* API images at S/2, only with NR_ANTI_ALIASING (each may be NULL if not wanted) */
+    float *out_rgb;   /* [B,3,S/2,S/2] */
+    float *out_alpha; /* [B,S/2,S/2]   */
+    float *out_depth; /* [B,S/2,S/2]   */
+    void *workspace; /* nr_b200_forward_workspace_bytes() bytes, 16-byte aligned */
+    size_t workspace_bytes;
+} nr_b200_forward_args;
+
+typedef struct nr_b200_backward_args {
+    uint32_t struct_size;
+    uint32_t flags; /* same flag set as the forward call that produced the maps */
+    int32_t batch_size, num_faces, raster_size, texture_size;
+    double eps; /* edge-distance epsilon (rasterize.py:650) and texture clamp epsilon -- the reference uses one value */
+    const float *faces;    /* [B,F,3,3] as given to the forward call */
+    const float *textures; /* may be NULL: only its shape matters for the backward pass */
+    const int32_t *face_index_map; /* saved maps from nr_b200_forward */
+    const float *weight_map;
+    const float *depth_map;
+    const float *rgb_map;
+    /* upstream gradients in API layout (size S, or S/2 with NR_ANTI_ALIASING); NULL = zeros */
+    const float *grad_rgb;   /* [B,3,H,W] */
+    const float *grad_alpha; /* [B,H,W]   */
+    const float *grad_depth; /* [B,H,W]   */
+    float *grad_faces;    /* [B,F,3,3]                 */
+    float *grad_textures; /* [B,F,ts,ts,ts,3] or NULL  */
+    void *workspace;
+    size_t workspace_bytes;
+} nr_b200_backward_args;
+
+/* ABI version of the loaded library (== NR_B200_ABI_VERSION it was built with). */
+NR_B200_API int nr_b200_abi_version(void);
+NR_B200_API const char *nr_b200_error_string(int code);
+
+/* Scratch sizes (bytes).  Pure host arithmetic; safe to call without a GPU. */
+NR_B200_API size_t nr_b200_forward_workspace_bytes(int32_t batch_size, int32_t num_faces, int32_t raster_size, int32_t texture_size,
+                                       uint32_t flags);
+NR_B200_API size_t nr_b200_backward_workspace_bytes(int32_t batch_size, int32_t num_faces, int32_t raster_size,
+                                        int32_t texture_size, uint32_t flags);
+
+NR_B200_API int nr_b200_forward(const nr_b200_forward_args *args, void *cuda_stream);
+NR_B200_API int nr_b200_backward(const nr_b200_backward_args *args, void *cuda_stream);
+
+/* Number of kernels the last forward/backward call on this thread launched (for launch accounting). */
+NR_B200_API int nr_b200_last_launch_count(void);
+
+/* Optional per-kernel timing: when enabled (per host thread) every kernel launch of forward/backward is bracketed
+ * by CUDA events on the launching stream.  nr_b200_read_profile synchronises on them, writes up to max_entries
+ * durations (milliseconds) to `ms` and the kernel names as a NUL-separated list to `names`, clears the record and
+ * returns the number of entries.  Used by bench.py for the roofline of the dominant kernel; off by default. */
+NR_B200_API void nr_b200_set_profiling(int enabled);
+NR_B200_API int nr_b200_read_profile(char *names, size_t names_bytes, float *ms, int max_entries);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NR_B200_H_ */

@@ -1,0 +1,411 @@
+// nr_forward.cu -- forward rasterization for sm_100a.
+//
+// Replaces Rasterize.forward_gpu (reference neural_renderer/rasterize.py:467-513: K1 :242-277, K2 :281-359,
+// K4 :372-438, alpha/background :440-465) and the transpose / flip / 2x2 pooling of rasterize_rgbad (:953-969).
+//
+// The reference tests every face against every pixel (B*S*S*F face tests).  Here:
+//
+//   k_face_bbox   one thread per face: back-face / non-finite cull and a conservative pixel bounding box
+//                 (8 bytes per face) plus one union box per 256-face chunk -- the only scratch the pass needs.
+//   k_raster_tile one CTA per 64x64 screen tile (the z-tile lives in shared memory as 64-bit (zp, face) keys):
+//                   1. warps pull 32-face groups, cull them against the tile by chunk box then face box,
+//                   2. survivors get their exact K1 inverse computed once (lane-parallel) into a per-warp ring,
+//                   3. each survivor's clipped box is swept 8x4 pixels at a time with the reference's three
+//                      edge tests; passing (face, pixel) fragments are warp-compacted into a per-warp queue,
+//                   4. full warps of fragments evaluate the exact barycentric / perspective-depth expression and
+//                      min-reduce (ordered zp bits << 32 | face index) into the z-tile -- lexicographic
+//                      (zp, fn) minimum == the reference's strict `<` over ascending face index,
+//                   5. after one barrier every thread resolves pixels: recompute the winner's weights with the
+//                      same expression tree, sample its ts^3 texture (K4), composite the background, and stream
+//                      all maps out as planar, row-flipped (image orientation) coalesced rows; with
+//                      anti-aliasing each thread owns a 2x2 quad and also emits the pooled API pixel.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "nr_b200.h"
+#include "nr_math.cuh"
+#include "nr_internal.h"
+#include "nr_bbox.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kTilePix = 4096;
+constexpr int kRing = 64;      // per-warp ring of survivor records
+constexpr int kRecWords = 20;  // inv[9] z[3] | x0 y0 x1 y1 | x2 y2 fn box
+
+struct FwdParams {
+    const float* faces;
+    const float* textures;
+    const float* bg_batch;
+    const uint2* bbox;
+    const uint2* chunk_bbox;
+    int32_t* fim;
+    float* wmap;
+    float* dmap;
+    float* rgb;
+    float* alpha;
+    float* out_rgb;
+    float* out_alpha;
+    float* out_depth;
+    int B, F, S, ts, nchunks;
+    int tw_log2, th_log2, tiles_x;
+    uint32_t flags;
+    float near_lo, far_cmp, far_val, tex_cmp, tex_val;
+    float bg[3];
+};
+
+// ---------------------------------------------------------------------------------------------- k_raster_tile
+struct __align__(16) TileShared {
+    unsigned long long zbuf[kTilePix];        // 32 KB  (ordered zp bits << 32 | face index), ~0 = empty
+    float ring[kWarps][kRing][kRecWords];     // 40 KB  per-warp survivor records
+    uint32_t fq[kWarps][64];                  //  2 KB  per-warp fragment ring: slot << 12 | pixel-in-tile
+    float xp[64];
+    float yp[64];
+    int next_group;
+};
+
+struct Shaded {
+    int fim;
+    float w0, w1, w2, depth, r, g, b, alpha;
+};
+
+__device__ __forceinline__ Shaded shade_pixel(const FwdParams& p, int b, unsigned long long key, int xi, int yi,
+                                              float bgr, float bgg, float bgb) {
+    Shaded o;
+    if (key == ~0ull) {
+        o.fim = -1; o.w0 = o.w1 = o.w2 = 0.0f; o.depth = p.far_val; o.r = bgr; o.g = bgg; o.b = bgb; o.alpha = 0.0f;
+        return o;
+    }
+    const int fn = (int)(uint32_t)(key & 0xFFFFFFFFull);
+    const float zp = nr::ordered_to_float((uint32_t)(key >> 32));
+    const float* v = p.faces + ((size_t)b * p.F + fn) * 9;
+    float c[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) c[k] = __ldg(v + k);
+    const float fS = (float)p.S;
+    float inv[9], w[3];
+    nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS), nr::to_pixel(c[4], fS),
+                     nr::to_pixel(c[6], fS), nr::to_pixel(c[7], fS), inv);
+    (void)nr::weights_and_depth(inv, (float)xi, (float)yi, c[2], c[5], c[8], w);
+    o.fim = fn; o.w0 = w[0]; o.w1 = w[1]; o.w2 = w[2]; o.depth = zp; o.alpha = 1.0f;
+    o.r = o.g = o.b = 0.0f;
+    if (p.flags & NR_RETURN_RGB) {
+        float z0 = c[2], z1 = c[5], z2 = c[8];
+        if (p.flags & NR_TEX_Z_BATCH0) {  // rasterize.py:389 -- vertex depths of batch item 0
+            const float* v0 = p.faces + (size_t)fn * 9;
+            z0 = __ldg(v0 + 2); z1 = __ldg(v0 + 5); z2 = __ldg(v0 + 8);
+        }
+        const int ts = p.ts;
+        const nr::TexCoord tc = nr::texture_coords(w, zp, z0, z1, z2, ts, p.tex_cmp, p.tex_val);
+        const float* tex = p.textures + ((size_t)b * p.F + fn) * (size_t)(ts * ts * ts) * 3;
+        float r = 0.0f, g = 0.0f, bl = 0.0f;
+#pragma unroll
+        for (int pn = 0; pn < 8; pn++) {
+            const float cw = nr::corner_weight(tc, pn);
+            const float* t = tex + nr::corner_index(tc, pn, ts) * 3;
+            r = __fmaf_rn(cw, __ldg(t + 0), r);
+            g = __fmaf_rn(cw, __ldg(t + 1), g);
+            bl = __fmaf_rn(cw, __ldg(t + 2), bl);
+        }
+        o.r = r; o.g = g; o.b = bl;
+    }
+    return o;
+}
+
+template <bool kAA>
+__global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant__ FwdParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int tw = 1 << p.tw_log2, th = 1 << p.th_log2;
+    const int tx0 = (tile % p.tiles_x) << p.tw_log2, ty0 = (tile / p.tiles_x) << p.th_log2;
+    const int tx1 = min(tx0 + tw, p.S) - 1, ty1 = min(ty0 + th, p.S) - 1;  // inclusive
+    const int npix = tw * th;
+
+    for (int i = tid; i < npix; i += kThreads) sm.zbuf[i] = ~0ull;
+    if (tid < 64) {
+        // rasterize.py:291-292  xp = (2*xi + 1 - is) / is, evaluated in double and rounded to float
+        const double dS = (double)p.S;
+        sm.xp[tid] = (float)((double)(2 * (tx0 + tid) + 1 - p.S) / dS);
+        sm.yp[tid] = (float)((double)(2 * (ty0 + tid) + 1 - p.S) / dS);
+    }
+    if (tid == 0) sm.next_group = 0;
+    __syncthreads();
+
+    // ------------------------------------------------------------------ raster phase (warp-autonomous)
+    {
+        const int ngroups = (p.F + 31) >> 5;
+        const uint2* bbox = p.bbox + (size_t)b * p.F;
+        const uint2* cbox = p.chunk_bbox + (size_t)b * p.nchunks;
+        float(*ring)[kRecWords] = sm.ring[warp];
+        uint32_t* fq = sm.fq[warp];
+        unsigned long long* zbuf = sm.zbuf;
+        const float fS = (float)p.S;
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        int ring_head = 0, fq_head = 0, fq_n = 0;
+
+        auto drain = [&](int cnt) {
+            if (lane < cnt) {
+                const uint32_t e = fq[(fq_head + lane) & 63];
+                const int slot = (int)(e >> 12), pix = (int)(e & 4095u);
+                const float4* r4 = reinterpret_cast<const float4*>(ring[slot]);
+                const float4 a = r4[0], bb = r4[1], cc = r4[2];
+                const int fn = __float_as_int(ring[slot][18]);
+                const float inv[9] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w, cc.x};
+                const int lx = pix & (tw - 1), ly = pix >> p.tw_log2;
+                float w[3];
+                const float zp = nr::weights_and_depth(inv, (float)(tx0 + lx), (float)(ty0 + ly), cc.y, cc.z, cc.w, w);
+                // rasterize.py:331 + :334 against the initial depth_min = far; NaN fails both (never wins)
+                if (zp > p.near_lo && zp < p.far_cmp) {
+                    const unsigned long long key = ((unsigned long long)nr::float_to_ordered(zp) << 32) | (uint32_t)fn;
+                    unsigned long long* addr = zbuf + pix;
+                    if (key < *reinterpret_cast<volatile unsigned long long*>(addr)) atomicMin(addr, key);
+                }
+            }
+            fq_head = (fq_head + cnt) & 63;
+            fq_n -= cnt;
+            __syncwarp();  // queue entries / ring records just read may be overwritten by the next push
+        };
+
+        while (true) {
+            int g = 0;
+            if (lane == 0) g = atomicAdd(&sm.next_group, 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= ngroups) break;
+            {   // chunk-level cull (uniform)
+                const uint2 cb = __ldg(cbox + (g >> 3));
+                if (unpack_lo(cb.x) > tx1 || unpack_hi(cb.x) < tx0 || unpack_lo(cb.y) > ty1 || unpack_hi(cb.y) < ty0) continue;
+            }
+            const int f = (g << 5) + lane;
+            bool pass = false;
+            int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
+            if (f < p.F) {
+                const uint2 bb = __ldg(bbox + f);
+                bx0 = max(unpack_lo(bb.x), tx0); bx1 = min(unpack_hi(bb.x), tx1);
+                by0 = max(unpack_lo(bb.y), ty0); by1 = min(unpack_hi(bb.y), ty1);
+                pass = (bx0 <= bx1) && (by0 <= by1);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (m == 0u) continue;
+            const int nsurv = __popc(m);
+            // records of faces that still have queued fragments must not be overwritten
+            if (fq_n > 0) {
+                const int oldest = (int)(fq[fq_head] >> 12);
+                // live records = distance from the oldest pending fragment's slot to the head, in [1, kRing]
+                if ((((ring_head - oldest - 1) & (kRing - 1)) + 1) + nsurv > kRing) drain(fq_n);
+            }
+            if (pass) {
+                const int slot = (ring_head + __popc(m & lt_mask)) & (kRing - 1);
+                const float* v = p.faces + ((size_t)b * p.F + f) * 9;
+                float c[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) c[k] = __ldg(v + k);
+                float inv[9];
+                nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS),
+                                 nr::to_pixel(c[4], fS), nr::to_pixel(c[6], fS), nr::to_pixel(c[7], fS), inv);
+                float4* r4 = reinterpret_cast<float4*>(ring[slot]);
+                r4[0] = make_float4(inv[0], inv[1], inv[2], inv[3]);
+                r4[1] = make_float4(inv[4], inv[5], inv[6], inv[7]);
+                r4[2] = make_float4(inv[8], c[2], c[5], c[8]);
+                r4[3] = make_float4(c[0], c[1], c[3], c[4]);
+                const uint32_t box = (uint32_t)(bx0 - tx0) | ((uint32_t)(bx1 - tx0) << 8) | ((uint32_t)(by0 - ty0) << 16) |
+                                     ((uint32_t)(by1 - ty0) << 24);
+                r4[4] = make_float4(c[6], c[7], __int_as_float(f), __uint_as_float(box));
+            }
+            __syncwarp();
+            for (int j = 0; j < nsurv; j++) {
+                const int slot = (ring_head + j) & (kRing - 1);
+                const float4* r4 = reinterpret_cast<const float4*>(ring[slot]);
+                const float4 q0 = r4[3], q1 = r4[4];
+                const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y;
+                const uint32_t box = __float_as_uint(q1.w);
+                const int lx0 = box & 0xFF, lx1 = (box >> 8) & 0xFF, ly0 = (box >> 16) & 0xFF, ly1 = box >> 24;
+                const float dx10 = __fsub_rn(x1, x0), dy10 = __fsub_rn(y1, y0), dx21 = __fsub_rn(x2, x1),
+                            dy21 = __fsub_rn(y2, y1), dx02 = __fsub_rn(x0, x2), dy02 = __fsub_rn(y0, y2);
+                for (int oy = ly0; oy <= ly1; oy += 4) {
+                    const int ly = oy + (lane >> 3);
+                    for (int ox = lx0; ox <= lx1; ox += 8) {
+                        const int lx = ox + (lane & 7);
+                        bool in = (lx <= lx1) && (ly <= ly1);
+                        if (in) in = nr::inside_face(sm.xp[lx], sm.yp[ly], x0, y0, x1, y1, x2, y2, dx10, dy10, dx21, dy21, dx02, dy02);
+                        const uint32_t mi = __ballot_sync(0xffffffffu, in);
+                        if (mi == 0u) continue;
+                        if (in) fq[(fq_head + fq_n + __popc(mi & lt_mask)) & 63] = ((uint32_t)slot << 12) | (uint32_t)((ly << p.tw_log2) + lx);
+                        fq_n += __popc(mi);
+                        __syncwarp();
+                        if (fq_n >= 32) drain(32);
+                    }
+                }
+            }
+            ring_head = (ring_head + nsurv) & (kRing - 1);
+        }
+        if (fq_n > 0) drain(fq_n);
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ resolve + shade + stream out
+    const int S = p.S;
+    float bgr = p.bg[0], bgg = p.bg[1], bgb = p.bg[2];
+    if (p.flags & NR_BG_PER_BATCH) {
+        bgr = __ldg(p.bg_batch + 3 * b + 0); bgg = __ldg(p.bg_batch + 3 * b + 1); bgb = __ldg(p.bg_batch + 3 * b + 2);
+    }
+    const size_t plane = (size_t)S * S;
+    const bool want_rgb = (p.flags & NR_RETURN_RGB) != 0;
+    if (!kAA) {
+        for (int pix = tid; pix < npix; pix += kThreads) {
+            const int lx = pix & (tw - 1), ly = pix >> p.tw_log2;
+            const int xi = tx0 + lx, yi = ty0 + ly;
+            if (xi >= S || yi >= S) continue;
+            const Shaded s = shade_pixel(p, b, sm.zbuf[pix], xi, yi, bgr, bgg, bgb);
+            const size_t o = (size_t)b * plane + (size_t)(S - 1 - yi) * S + xi;  // image orientation
+            p.fim[o] = s.fim;
+            p.dmap[o] = s.depth;
+            float* wm = p.wmap + (size_t)b * 3 * plane + (size_t)(S - 1 - yi) * S + xi;
+            wm[0] = s.w0; wm[plane] = s.w1; wm[2 * plane] = s.w2;
+            if (p.alpha) p.alpha[o] = s.alpha;
+            if (want_rgb) {
+                float* rm = p.rgb + (size_t)b * 3 * plane + (size_t)(S - 1 - yi) * S + xi;
+                rm[0] = s.r; rm[plane] = s.g; rm[2 * plane] = s.b;
+            }
+        }
+    } else {
+        const int qw_log2 = p.tw_log2 - 1;
+        const int nquad = npix >> 2;
+        const int H = S >> 1;
+        const size_t oplane = (size_t)H * H;
+        for (int q = tid; q < nquad; q += kThreads) {
+            const int lx = (q & ((1 << qw_log2) - 1)) << 1, ly = (q >> qw_log2) << 1;
+            const int xi = tx0 + lx, yi = ty0 + ly;
+            if (xi >= S || yi >= S) continue;  // S is even: quads are entirely in or out
+            // image-orientation quad: top row = raster row yi+1
+            const Shaded tl = shade_pixel(p, b, sm.zbuf[((ly + 1) << p.tw_log2) + lx], xi, yi + 1, bgr, bgg, bgb);
+            const Shaded tr = shade_pixel(p, b, sm.zbuf[((ly + 1) << p.tw_log2) + lx + 1], xi + 1, yi + 1, bgr, bgg, bgb);
+            const Shaded bl = shade_pixel(p, b, sm.zbuf[(ly << p.tw_log2) + lx], xi, yi, bgr, bgg, bgb);
+            const Shaded br = shade_pixel(p, b, sm.zbuf[(ly << p.tw_log2) + lx + 1], xi + 1, yi, bgr, bgg, bgb);
+            const size_t otop = (size_t)b * plane + (size_t)(S - 2 - yi) * S + xi;  // row of raster yi+1
+            const size_t obot = otop + S;
+            *reinterpret_cast<int2*>(p.fim + otop) = make_int2(tl.fim, tr.fim);
+            *reinterpret_cast<int2*>(p.fim + obot) = make_int2(bl.fim, br.fim);
+            *reinterpret_cast<float2*>(p.dmap + otop) = make_float2(tl.depth, tr.depth);
+            *reinterpret_cast<float2*>(p.dmap + obot) = make_float2(bl.depth, br.depth);
+            float* wt = p.wmap + (size_t)b * 3 * plane + (size_t)(S - 2 - yi) * S + xi;
+            *reinterpret_cast<float2*>(wt) = make_float2(tl.w0, tr.w0);
+            *reinterpret_cast<float2*>(wt + S) = make_float2(bl.w0, br.w0);
+            *reinterpret_cast<float2*>(wt + plane) = make_float2(tl.w1, tr.w1);
+            *reinterpret_cast<float2*>(wt + plane + S) = make_float2(bl.w1, br.w1);
+            *reinterpret_cast<float2*>(wt + 2 * plane) = make_float2(tl.w2, tr.w2);
+            *reinterpret_cast<float2*>(wt + 2 * plane + S) = make_float2(bl.w2, br.w2);
+            if (p.alpha) {
+                *reinterpret_cast<float2*>(p.alpha + otop) = make_float2(tl.alpha, tr.alpha);
+                *reinterpret_cast<float2*>(p.alpha + obot) = make_float2(bl.alpha, br.alpha);
+            }
+            const size_t oo = (size_t)(H - 1 - (yi >> 1)) * H + (xi >> 1);
+            if (want_rgb) {
+                float* rt = p.rgb + (size_t)b * 3 * plane + (size_t)(S - 2 - yi) * S + xi;
+                *reinterpret_cast<float2*>(rt) = make_float2(tl.r, tr.r);
+                *reinterpret_cast<float2*>(rt + S) = make_float2(bl.r, br.r);
+                *reinterpret_cast<float2*>(rt + plane) = make_float2(tl.g, tr.g);
+                *reinterpret_cast<float2*>(rt + plane + S) = make_float2(bl.g, br.g);
+                *reinterpret_cast<float2*>(rt + 2 * plane) = make_float2(tl.b, tr.b);
+                *reinterpret_cast<float2*>(rt + 2 * plane + S) = make_float2(bl.b, br.b);
+                if (p.out_rgb) {
+                    float* orgb = p.out_rgb + (size_t)b * 3 * oplane + oo;
+                    orgb[0] = (((tl.r + tr.r) + bl.r) + br.r) * 0.25f;
+                    orgb[oplane] = (((tl.g + tr.g) + bl.g) + br.g) * 0.25f;
+                    orgb[2 * oplane] = (((tl.b + tr.b) + bl.b) + br.b) * 0.25f;
+                }
+            }
+            if (p.out_alpha) p.out_alpha[(size_t)b * oplane + oo] = (((tl.alpha + tr.alpha) + bl.alpha) + br.alpha) * 0.25f;
+            if (p.out_depth) p.out_depth[(size_t)b * oplane + oo] = (((tl.depth + tr.depth) + bl.depth) + br.depth) * 0.25f;
+        }
+    }
+}
+
+inline float float_le(double d) {  // largest float <= d
+    float f = (float)d;
+    if ((double)f > d) f = nextafterf(f, -INFINITY);
+    return f;
+}
+inline float float_ge(double d) {  // smallest float >= d
+    float f = (float)d;
+    if ((double)f < d) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+}  // namespace
+
+extern "C" size_t nr_b200_forward_workspace_bytes(int32_t B, int32_t F, int32_t S, int32_t ts, uint32_t flags) {
+    (void)S; (void)ts; (void)flags;
+    return bbox_workspace_bytes(B, F);
+}
+
+extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream) {
+    nr_internal::launch_count() = 0;
+    if (!a || a->struct_size != sizeof(nr_b200_forward_args)) return NR_ERR_INVALID_ARG;
+    const int B = a->batch_size, F = a->num_faces, S = a->raster_size, ts = a->texture_size;
+    const uint32_t flags = a->flags;
+    if (B <= 0 || F <= 0 || S <= 0) return NR_ERR_INVALID_ARG;
+    if (!(flags & (NR_RETURN_RGB | NR_RETURN_ALPHA | NR_RETURN_DEPTH))) return NR_ERR_INVALID_ARG;  // rasterize.py:25-27
+    if (!a->faces || !a->face_index_map || !a->weight_map || !a->depth_map) return NR_ERR_INVALID_ARG;
+    if (flags & NR_RETURN_RGB) {
+        if (!a->textures || !a->rgb_map || ts < 2) return NR_ERR_INVALID_ARG;
+        if ((flags & NR_BG_PER_BATCH) && !a->background_batch) return NR_ERR_INVALID_ARG;
+    }
+    if ((flags & NR_ANTI_ALIASING) && (S & 1)) return NR_ERR_INVALID_ARG;
+    if (S > 32767 || B > 65535) return NR_ERR_UNSUPPORTED;
+    if ((size_t)F > (size_t)0x7FFFFFFF - 64) return NR_ERR_UNSUPPORTED;
+    const size_t need = nr_b200_forward_workspace_bytes(B, F, S, ts, flags);
+    if (!a->workspace || a->workspace_bytes < need || ((uintptr_t)a->workspace & 15)) return NR_ERR_WORKSPACE;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+
+    const int nchunks = (F + kChunk - 1) / kChunk;
+    uint2* bbox = (uint2*)a->workspace;
+    uint2* cbox = (uint2*)((char*)a->workspace + nr_align_up((size_t)B * F * sizeof(uint2), 256));
+
+    {
+        nr_internal::LaunchScope ls("k_face_bbox", stream);
+        k_face_bbox<<<dim3(nchunks, B), kChunk, 0, stream>>>(a->faces, F, S, nchunks, bbox, cbox);
+    }
+
+    FwdParams p{};
+    p.faces = a->faces; p.textures = a->textures; p.bg_batch = a->background_batch;
+    p.bbox = bbox; p.chunk_bbox = cbox;
+    p.fim = a->face_index_map; p.wmap = a->weight_map; p.dmap = a->depth_map; p.rgb = a->rgb_map; p.alpha = a->alpha_map;
+    p.out_rgb = a->out_rgb; p.out_alpha = a->out_alpha; p.out_depth = a->out_depth;
+    p.B = B; p.F = F; p.S = S; p.ts = ts; p.nchunks = nchunks;
+    int tl = 6;  // 64x64 tiles; shrink for small rasters so that a tile is not mostly padding
+    while (tl > 3 && (1 << (tl - 1)) >= S) tl--;
+    p.tw_log2 = tl; p.th_log2 = tl;
+    p.tiles_x = (S + (1 << tl) - 1) >> tl;
+    const int tiles_y = p.tiles_x;
+    p.flags = flags;
+    p.near_lo = float_le(a->near_);
+    p.far_cmp = fminf(float_ge(a->far_), (float)a->far_);
+    p.far_val = (float)a->far_;
+    const double tmax = (double)(ts - 1) - a->eps;
+    p.tex_cmp = float_le(tmax);
+    p.tex_val = (float)tmax;
+    p.bg[0] = a->background[0]; p.bg[1] = a->background[1]; p.bg[2] = a->background[2];
+
+    const size_t smem = sizeof(TileShared);
+    cudaError_t e;
+    if (flags & NR_ANTI_ALIASING) {
+        e = cudaFuncSetAttribute(k_raster_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return NR_ERR_CUDA;
+        nr_internal::LaunchScope ls("k_raster_tile", stream);
+        k_raster_tile<true><<<dim3(p.tiles_x * tiles_y, B), kThreads, smem, stream>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(k_raster_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return NR_ERR_CUDA;
+        nr_internal::LaunchScope ls("k_raster_tile", stream);
+        k_raster_tile<false><<<dim3(p.tiles_x * tiles_y, B), kThreads, smem, stream>>>(p);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? NR_OK : NR_ERR_CUDA;
+}

@@ -1,0 +1,324 @@
+"""Host-side mirror of the reference's rasterizer interface (neural_renderer/rasterize.py) on top of the C ABI.
+
+Same names, argument order, defaults and error conditions as the reference:
+
+  rasterize_rgbad        rasterize.py:900-977
+  rasterize              rasterize.py:980-1008
+  rasterize_silhouettes  rasterize.py:1011-1034
+  rasterize_depth        rasterize.py:1037-1060
+  Rasterize              rasterize.py:19-897   (function object; returns un-flipped NHWC maps like forward_gpu)
+  use_unsafe_rasterizer  rasterize.py:1063-1065
+
+Tensors are CUDA `torch.Tensor`s instead of chainer Variables / cupy arrays; PyTorch only provides device memory,
+the current stream and autograd bookkeeping -- all arithmetic happens in libnr_b200.so (hand-written sm_100a CUDA).
+There is no CPU path (the reference raises NotImplementedError for CPU arrays as well, rasterize.py:893-897).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+
+DEFAULT_IMAGE_SIZE = 256
+DEFAULT_ANTI_ALIASING = True
+DEFAULT_NEAR = 0.1
+DEFAULT_FAR = 100
+DEFAULT_EPS = 1e-4
+DEFAULT_BACKGROUND_COLOR = (0, 0, 0)
+USE_UNSAFE_IMPLEMENTATION = False
+
+# rasterize.py:389 fetches the vertex depths for texture sampling from batch item 0.  Reference-exact by default;
+# NEURAL_RENDERER_B200_FIX_TEXTURE_DEPTH=1 (or set_reference_exact(False)) samples with each item's own depths.
+_REFERENCE_EXACT = not int(os.environ.get("NEURAL_RENDERER_B200_FIX_TEXTURE_DEPTH", "0"))
+
+
+def set_reference_exact(flag):
+    global _REFERENCE_EXACT
+    _REFERENCE_EXACT = bool(flag)
+
+
+def use_unsafe_rasterizer(flag):
+    """Accepted for interface compatibility (rasterize.py:1063).  The reference's 'unsafe' scanline/spin-lock
+    variant is an alternative implementation of the same maps with arrival-order tie breaks; this package has a
+    single deterministic forward path, so the flag changes nothing."""
+    global USE_UNSAFE_IMPLEMENTATION
+    USE_UNSAFE_IMPLEMENTATION = bool(flag)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _check_inputs(faces, textures, return_rgb):
+    # rasterize.py:66-90 (chainer type_check) -> TypeError / ValueError with the same conditions
+    if not isinstance(faces, torch.Tensor):
+        raise TypeError("faces must be a torch.Tensor")
+    if not faces.is_floating_point():
+        raise TypeError("faces must be floating point")
+    if faces.dim() != 4 or faces.shape[2] != 3 or faces.shape[3] != 3:
+        raise ValueError("faces must have shape [batch size, num faces, 3, 3], got %s" % (tuple(faces.shape),))
+    if return_rgb:
+        if not isinstance(textures, torch.Tensor):
+            raise TypeError("textures are required to draw RGB")
+        if not textures.is_floating_point():
+            raise TypeError("textures must be floating point")
+        if (textures.dim() != 6 or textures.shape[2] < 2 or textures.shape[2] != textures.shape[3]
+                or textures.shape[3] != textures.shape[4] or textures.shape[5] != 3
+                or textures.shape[0] != faces.shape[0] or textures.shape[1] != faces.shape[1]):
+            raise ValueError("textures must have shape [batch size, num faces, ts, ts, ts, 3] with ts >= 2 and match "
+                             "faces, got %s" % (tuple(textures.shape),))
+    if not faces.is_cuda or (return_rgb and not textures.is_cuda):
+        raise NotImplementedError("neural_renderer_b200 has no CPU implementation (inputs must be CUDA tensors)")
+
+
+class _Config:
+    __slots__ = ("S", "aa", "near", "far", "eps", "bg", "bg_batch", "flags", "reference_exact")
+
+
+def _make_config(image_size, anti_aliasing, near, far, eps, background_color, return_rgb, return_alpha, return_depth,
+                 device, batch_size):
+    if not any((return_rgb, return_alpha, return_depth)):
+        raise Exception("nothing to draw")  # rasterize.py:25-27 raises a bare Exception
+    cfg = _Config()
+    cfg.aa = bool(anti_aliasing)
+    cfg.S = int(image_size) * 2 if cfg.aa else int(image_size)
+    cfg.near, cfg.far, cfg.eps = float(near), float(far), float(eps)
+    flags = 0
+    if return_rgb:
+        flags |= _lib.NR_RETURN_RGB
+    if return_alpha:
+        flags |= _lib.NR_RETURN_ALPHA
+    if return_depth:
+        flags |= _lib.NR_RETURN_DEPTH
+    if cfg.aa:
+        flags |= _lib.NR_ANTI_ALIASING
+    cfg.reference_exact = _REFERENCE_EXACT
+    if cfg.reference_exact:
+        flags |= _lib.NR_TEX_Z_BATCH0
+    cfg.bg = (0.0, 0.0, 0.0)
+    cfg.bg_batch = None
+    if return_rgb:
+        bg = background_color
+        if isinstance(bg, torch.Tensor):
+            bg = bg.detach().to(dtype=torch.float32)
+        else:
+            bg = torch.as_tensor(bg, dtype=torch.float32)
+        if bg.dim() == 1 and bg.numel() == 3:
+            cfg.bg = tuple(float(v) for v in bg.tolist())
+        elif bg.dim() == 2 and bg.shape[1] == 3 and bg.shape[0] == batch_size:  # rasterize.py:464-465
+            cfg.bg_batch = bg.to(device).contiguous()
+            flags |= _lib.NR_BG_PER_BATCH
+        else:
+            raise ValueError("background_color must have shape (3,) or (batch size, 3)")
+    cfg.flags = flags
+    return cfg
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _RasterizeFunction(torch.autograd.Function):
+    """autograd node of the hot path: forward = nr_b200_forward, backward = nr_b200_backward.
+
+    Outputs are the API images (planar, image orientation, pooled when anti-aliasing) plus the raster-resolution
+    maps (returned non-differentiable so tests / the `Rasterize` object can look at them)."""
+
+    @staticmethod
+    def forward(ctx, faces, textures, cfg):
+        lib = _lib.load()
+        dev = faces.device
+        faces_c = faces.detach().contiguous()
+        tex_c = textures.detach().contiguous() if textures is not None else None
+        B, F = faces_c.shape[:2]
+        S = cfg.S
+        ts = int(tex_c.shape[2]) if tex_c is not None else 0
+        want_rgb = bool(cfg.flags & _lib.NR_RETURN_RGB)
+        want_alpha = bool(cfg.flags & _lib.NR_RETURN_ALPHA)
+        want_depth = bool(cfg.flags & _lib.NR_RETURN_DEPTH)
+        with torch.cuda.device(dev):
+            fim = torch.empty((B, S, S), dtype=torch.int32, device=dev)
+            wmap = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
+            dmap = torch.empty((B, S, S), dtype=torch.float32, device=dev)
+            rgb_map = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev) if want_rgb else None
+            alpha_map = torch.empty((B, S, S), dtype=torch.float32, device=dev) if want_alpha else None
+            out_rgb = out_alpha = out_depth = None
+            if cfg.aa:
+                H = S // 2
+                if want_rgb:
+                    out_rgb = torch.empty((B, 3, H, H), dtype=torch.float32, device=dev)
+                if want_alpha:
+                    out_alpha = torch.empty((B, H, H), dtype=torch.float32, device=dev)
+                if want_depth:
+                    out_depth = torch.empty((B, H, H), dtype=torch.float32, device=dev)
+            ws_bytes = lib.nr_b200_forward_workspace_bytes(B, F, S, ts, cfg.flags)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            a = _lib.ForwardArgs()
+            a.struct_size = ctypes.sizeof(_lib.ForwardArgs)
+            a.flags = cfg.flags
+            a.batch_size, a.num_faces, a.raster_size, a.texture_size = B, F, S, ts
+            a.near_, a.far_, a.eps = cfg.near, cfg.far, cfg.eps
+            a.background[0], a.background[1], a.background[2] = cfg.bg
+            a.faces, a.textures, a.background_batch = _ptr(faces_c), _ptr(tex_c), _ptr(cfg.bg_batch)
+            a.face_index_map, a.weight_map, a.depth_map = _ptr(fim), _ptr(wmap), _ptr(dmap)
+            a.rgb_map, a.alpha_map = _ptr(rgb_map), _ptr(alpha_map)
+            a.out_rgb, a.out_alpha, a.out_depth = _ptr(out_rgb), _ptr(out_alpha), _ptr(out_depth)
+            a.workspace, a.workspace_bytes = _ptr(ws), ws_bytes
+            _lib.check(lib.nr_b200_forward(ctypes.byref(a), _stream_ptr(dev)))
+        ctx.cfg = cfg
+        ctx.ts = ts
+        ctx.tex_shape = tuple(textures.shape) if textures is not None else None
+        ctx.save_for_backward(faces_c, fim, wmap, dmap, rgb_map)
+        if cfg.aa:
+            rgb_o, alpha_o, depth_o = out_rgb, out_alpha, out_depth
+        else:
+            rgb_o, alpha_o, depth_o = rgb_map, alpha_map, (dmap if want_depth else None)
+        ctx.mark_non_differentiable(fim, wmap)
+        return rgb_o, alpha_o, depth_o, fim, wmap
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_alpha, g_depth, _g_fim, _g_wmap):
+        lib = _lib.load()
+        cfg = ctx.cfg
+        faces_c, fim, wmap, dmap, rgb_map = ctx.saved_tensors
+        dev = faces_c.device
+        B, F = faces_c.shape[:2]
+        want_rgb = bool(cfg.flags & _lib.NR_RETURN_RGB)
+
+        def prep(g, wanted):
+            if g is None or not wanted:
+                return None
+            return g.detach().to(torch.float32).contiguous()
+
+        g_rgb = prep(g_rgb, want_rgb)
+        g_alpha = prep(g_alpha, bool(cfg.flags & _lib.NR_RETURN_ALPHA))
+        g_depth = prep(g_depth, bool(cfg.flags & _lib.NR_RETURN_DEPTH))
+        with torch.cuda.device(dev):
+            grad_faces = torch.empty_like(faces_c)
+            grad_textures = torch.empty(ctx.tex_shape, dtype=torch.float32, device=dev) if want_rgb else None
+            ws_bytes = lib.nr_b200_backward_workspace_bytes(B, F, cfg.S, ctx.ts, cfg.flags)
+            ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+            a = _lib.BackwardArgs()
+            a.struct_size = ctypes.sizeof(_lib.BackwardArgs)
+            a.flags = cfg.flags
+            a.batch_size, a.num_faces, a.raster_size, a.texture_size = B, F, cfg.S, ctx.ts
+            a.eps = cfg.eps
+            a.faces, a.textures = _ptr(faces_c), None
+            a.face_index_map, a.weight_map, a.depth_map, a.rgb_map = _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(rgb_map)
+            a.grad_rgb, a.grad_alpha, a.grad_depth = _ptr(g_rgb), _ptr(g_alpha), _ptr(g_depth)
+            a.grad_faces, a.grad_textures = _ptr(grad_faces), _ptr(grad_textures)
+            a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+            _lib.check(lib.nr_b200_backward(ctypes.byref(a), _stream_ptr(dev)))
+        return grad_faces, grad_textures, None
+
+
+def _run(faces, textures, image_size, anti_aliasing, near, far, eps, background_color, return_rgb, return_alpha,
+         return_depth):
+    _check_inputs(faces, textures, return_rgb)
+    if faces.dtype != torch.float32:
+        faces = faces.float()
+    if return_rgb and textures.dtype != torch.float32:
+        textures = textures.float()
+    cfg = _make_config(image_size, anti_aliasing, near, far, eps, background_color, return_rgb, return_alpha,
+                       return_depth, faces.device, faces.shape[0])
+    return _RasterizeFunction.apply(faces, textures if return_rgb else None, cfg)
+
+
+def rasterize_rgbad(
+        faces,
+        textures=None,
+        image_size=DEFAULT_IMAGE_SIZE,
+        anti_aliasing=DEFAULT_ANTI_ALIASING,
+        near=DEFAULT_NEAR,
+        far=DEFAULT_FAR,
+        eps=DEFAULT_EPS,
+        background_color=DEFAULT_BACKGROUND_COLOR,
+        return_rgb=True,
+        return_alpha=True,
+        return_depth=True,
+):
+    """Generate RGB, alpha channel, and depth images from faces and textures (for RGB).  rasterize.py:900-977.
+
+    Returns {'rgb': [B,3,H,W], 'alpha': [B,H,W], 'depth': [B,H,W]} (None for the ones not requested)."""
+    rgb, alpha, depth, _, _ = _run(faces, textures, image_size, anti_aliasing, near, far, eps, background_color,
+                                   return_rgb, return_alpha, return_depth)
+    return {
+        'rgb': rgb if return_rgb else None,
+        'alpha': alpha if return_alpha else None,
+        'depth': depth if return_depth else None,
+    }
+
+
+def rasterize(
+        faces,
+        textures,
+        image_size=DEFAULT_IMAGE_SIZE,
+        anti_aliasing=DEFAULT_ANTI_ALIASING,
+        near=DEFAULT_NEAR,
+        far=DEFAULT_FAR,
+        eps=DEFAULT_EPS,
+        background_color=DEFAULT_BACKGROUND_COLOR,
+):
+    """RGB images [B,3,H,W] from faces and textures.  rasterize.py:980-1008."""
+    return rasterize_rgbad(
+        faces, textures, image_size, anti_aliasing, near, far, eps, background_color, True, False, False)['rgb']
+
+
+def rasterize_silhouettes(
+        faces,
+        image_size=DEFAULT_IMAGE_SIZE,
+        anti_aliasing=DEFAULT_ANTI_ALIASING,
+        near=DEFAULT_NEAR,
+        far=DEFAULT_FAR,
+        eps=DEFAULT_EPS,
+):
+    """Alpha channels [B,H,W] from faces.  rasterize.py:1011-1034."""
+    return rasterize_rgbad(faces, None, image_size, anti_aliasing, near, far, eps, None, False, True, False)['alpha']
+
+
+def rasterize_depth(
+        faces,
+        image_size=DEFAULT_IMAGE_SIZE,
+        anti_aliasing=DEFAULT_ANTI_ALIASING,
+        near=DEFAULT_NEAR,
+        far=DEFAULT_FAR,
+        eps=DEFAULT_EPS,
+):
+    """Depth images [B,H,W] from faces.  rasterize.py:1037-1060."""
+    return rasterize_rgbad(faces, None, image_size, anti_aliasing, near, far, eps, None, False, False, True)['depth']
+
+
+class Rasterize(object):
+    """The reference's function object (rasterize.py:19-64): `Rasterize(image_size, near, far, eps,
+    background_color, return_rgb, return_alpha, return_depth)(faces[, textures]) -> (rgb, alpha, depth)` with the
+    reference's internal conventions (NHWC rgb, rows NOT flipped, None for outputs not requested).  After the call
+    `face_index_map` / `weight_map` hold the raster maps in those same conventions (as the reference instance does)."""
+
+    def __init__(self, image_size, near, far, eps, background_color, return_rgb=False, return_alpha=False,
+                 return_depth=False):
+        if not any((return_rgb, return_alpha, return_depth)):
+            raise Exception("nothing to draw")
+        self.image_size = image_size
+        self.near = near
+        self.far = far
+        self.eps = eps
+        self.background_color = background_color
+        self.return_rgb = return_rgb
+        self.return_alpha = return_alpha
+        self.return_depth = return_depth
+        self.face_index_map = None
+        self.weight_map = None
+
+    def __call__(self, faces, textures=None):
+        rgb, alpha, depth, fim, wmap = _run(faces, textures, self.image_size, False, self.near, self.far, self.eps,
+                                            self.background_color, self.return_rgb, self.return_alpha,
+                                            self.return_depth)
+        self.face_index_map = fim.flip(1)
+        self.weight_map = wmap.permute(0, 2, 3, 1).flip(1)
+        rgb = rgb.permute(0, 2, 3, 1).flip(1) if self.return_rgb else None
+        alpha = alpha.flip(1) if self.return_alpha else None
+        depth = depth.flip(1) if self.return_depth else None
+        return rgb, alpha, depth

@@ -1,0 +1,80 @@
+"""`Renderer` facade with the reference's attribute bag and three render methods (renderer.py:8-107)."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import functional as F
+from .rasterize import rasterize, rasterize_depth, rasterize_silhouettes
+
+
+class Renderer(object):
+    def __init__(self):
+        # rendering
+        self.image_size = 256
+        self.anti_aliasing = True
+        self.background_color = [0, 0, 0]
+        self.fill_back = True
+
+        # camera
+        self.perspective = True
+        self.viewing_angle = 30
+        self.eye = [0, 0, -(1. / math.tan(math.radians(self.viewing_angle)) + 1)]
+        self.camera_mode = 'look_at'
+        self.camera_direction = [0, 0, 1]
+        self.near = 0.1
+        self.far = 100
+
+        # light
+        self.light_intensity_ambient = 0.5
+        self.light_intensity_directional = 0.5
+        self.light_color_ambient = [1, 1, 1]  # white
+        self.light_color_directional = [1, 1, 1]  # white
+        self.light_direction = [0, 1, 0]  # up-to-down
+
+        # rasterization
+        self.rasterizer_eps = 1e-3
+
+    def _transform(self, vertices):
+        if self.camera_mode == 'look_at':
+            vertices = F.look_at(vertices, self.eye)
+        elif self.camera_mode == 'look':
+            vertices = F.look(vertices, self.eye, self.camera_direction)
+        if self.perspective:
+            vertices = F.perspective(vertices, angle=self.viewing_angle)
+        return vertices
+
+    def render_silhouettes(self, vertices, faces):
+        if self.fill_back:
+            faces = torch.cat((faces, faces.flip(2)), dim=1)
+        vertices = self._transform(vertices)
+        faces = F.vertices_to_faces(vertices, faces)
+        # renderer.py:52 -- near / far / rasterizer_eps are NOT forwarded (module defaults apply)
+        return rasterize_silhouettes(faces, self.image_size, self.anti_aliasing)
+
+    def render_depth(self, vertices, faces):
+        if self.fill_back:
+            faces = torch.cat((faces, faces.flip(2)), dim=1)
+        vertices = self._transform(vertices)
+        faces = F.vertices_to_faces(vertices, faces)
+        return rasterize_depth(faces, self.image_size, self.anti_aliasing)  # renderer.py:72
+
+    def render(self, vertices, faces, textures):
+        if self.fill_back:
+            faces = torch.cat((faces, faces.flip(2)), dim=1)
+            textures = torch.cat((textures, textures.permute(0, 1, 4, 3, 2, 5)), dim=1)
+        faces_lighting = F.vertices_to_faces(vertices, faces)
+        textures = F.lighting(
+            faces_lighting,
+            textures,
+            self.light_intensity_ambient,
+            self.light_intensity_directional,
+            self.light_color_ambient,
+            self.light_color_directional,
+            self.light_direction)
+        vertices = self._transform(vertices)
+        faces = F.vertices_to_faces(vertices, faces)
+        return rasterize(
+            faces, textures, self.image_size, self.anti_aliasing, self.near, self.far, self.rasterizer_eps,
+            self.background_color)
