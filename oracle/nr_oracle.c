@@ -20,8 +20,9 @@
  *
  * Floating point: the reference is compiled by NVRTC with --fmad=true and no
  * fast-math.  The exact sequence of mul / add / fma / div.rn / rcp.rn that
- * results was read off the PTX of the reference strings (see DESIGN.md,
- * "pinned arithmetic") and is reproduced here with explicit fmaf(); everything
+ * results was read off the PTX *and SASS* of the reference strings (ptxas
+ * contracts PTX mul+add pairs that carry no .rn; see DESIGN.md, "pinned
+ * arithmetic") and is reproduced here with explicit fmaf(); everything
  * else is compiled with -ffp-contract=off so gcc cannot fuse on its own.
  * Where the reference promotes to double (literal `0.`, `1.`, `2.`, near, eps)
  * the same promotion is done here.
@@ -79,13 +80,14 @@ static void face_inv_one(const float *face, int is, float *inv /*9, zero-initial
     float n[9];
     n[0] = p1y - p2y;
     n[1] = p2x - p1x;
-    n[2] = p1x * p2y - p2x * p1y; /* mul, mul, sub -- not fused in the reference build */
+    /* a*b - c*d: PTX has mul, mul, sub without .rn; ptxas contracts it to fma(a, b, -RN(c*d)) in SASS */
+    n[2] = fmaf(p1x, p2y, -(p2x * p1y));
     n[3] = p2y - p0y;
     n[4] = p0x - p2x;
-    n[5] = p2x * p0y - p0x * p2y;
+    n[5] = fmaf(p2x, p0y, -(p0x * p2y));
     n[6] = p0y - p1y;
     n[7] = p1x - p0x;
-    n[8] = p0x * p1y - p1x * p0y;
+    n[8] = fmaf(p0x, p1y, -(p1x * p0y));
     /* p2x*(p0y-p1y) + p0x*(p1y-p2y) + p1x*(p2y-p0y)  ->  fma(p1x, d3, fma(p2x, d6, p0x*d0)) */
     float d = fmaf(p1x, n[3], fmaf(p2x, n[6], p0x * n[0]));
     for (int k = 0; k < 9; k++) inv[k] = n[k] / d;

@@ -24,7 +24,7 @@ def all_configs():
     # seeded random meshes
     c.append(cfg(32, 64, 2, NEAR, FAR, 1e-4, 1, 1, 1))
     for flags in ((1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)):
-        c.append(cfg(64, 200, 4, NEAR, FAR, 1e-4, *flags))
+        c.append(cfg(64, 200, 4 if flags[0] else 0, NEAR, FAR, 1e-4, *flags))
     c.append(cfg(100, 150, 3, NEAR, FAR, 1e-4, 1, 1, 1))   # raster size that is not a power of two
     c.append(cfg(128, 200, 4, NEAR, FAR, 1e-4, 1, 1, 1))   # used with anti_aliasing=True (image 64)
     c.append(cfg(64, 200, 2, 2.2, 3.0, 1e-4, 1, 1, 1))     # near / far rejection

@@ -46,7 +46,8 @@ def _inputs(kind, B, F, ts, seed):
 
 
 def _run_product(faces, tex, image_size, aa, near, far, eps, bg, flags, grads=None):
-    from neural_renderer_b200 import rasterize as R
+    import importlib
+    R = importlib.import_module("neural_renderer_b200.rasterize")
     dev = torch.device("cuda")
     f = torch.from_numpy(faces).to(dev).requires_grad_(True)
     t = torch.from_numpy(tex).to(dev).requires_grad_(True) if (tex is not None and flags[0]) else None
@@ -105,10 +106,15 @@ def test_forward_backward_vs_reference_kernels(case):
 
     # face_index_map: bit-exact (ours is stored in image orientation, the reference's un-flipped)
     assert torch.equal(got["fim"].flip(1), ref.fn.face_index_map), "face_index_map differs"
-    assert rel_err(np_(got["wmap"].permute(0, 2, 3, 1).flip(1)), np_(ref.fn.weight_map)) <= TOL
+    # the forward maps replay the reference's fp32 expression trees, so they are expected to match bit for bit
+    # (the contract only asks for 1e-4; the stricter check guards the pinned arithmetic of nr_math.cuh)
+    assert torch.equal(got["wmap"].permute(0, 2, 3, 1).flip(1), ref.fn.weight_map), "weight_map not bit-exact"
     for k in ("rgb", "alpha", "depth"):
         if ref[k] is not None:
             assert rel_err(np_(got[k]), np_(ref[k])) <= TOL, k
+            if not aa:
+                nbad = int((got[k] != ref[k]).sum().item())
+                assert nbad == 0, "%s: %d values differ in the last bits" % (k, nbad)
     gf, gt = ref.backward(grads.get("rgb"), grads.get("alpha"), grads.get("depth"))
     assert rel_err(np_(got["grad_faces"]), np_(gf)) <= TOL, "grad_faces"
     if flags[0]:
