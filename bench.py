@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=4, help="batch items of the workload timed on the CPU oracle")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="batch items of the workload timed on the CPU oracle")
     ap.add_argument("--no-side-measurements", action="store_true", help="skip cpu_baseline / reference_gpu / kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -1,7 +1,9 @@
 // nr_api.cu -- ABI bookkeeping entry points of libnr_b200.so (include/nr_b200.h).
 #include <string.h>
 
-#include <vector>
+#include <atomic>
+#include <mutex>
+#include <deque>
 
 #include "nr_b200.h"
 #include "nr_internal.h"
@@ -13,26 +15,32 @@ struct Timer {
     const char* name;
     cudaEvent_t start, stop;
 };
-thread_local bool g_profiling = false;
-thread_local std::vector<Timer> g_timers;
+// Process-wide (not thread-local): PyTorch runs autograd backward on its own engine thread, and the caller that
+// enabled profiling / reads the counters is the main thread.  The launch counter is bookkeeping, not control state.
+std::atomic<bool> g_profiling{false};
+std::mutex g_mu;
+std::deque<Timer> g_timers;  // deque: push_back keeps references to earlier records valid
+thread_local Timer* g_open = nullptr;
+int g_launches = 0;
 }  // namespace
 
-int& launch_count() {
-    static thread_local int n = 0;
-    return n;
-}
+int& launch_count() { return g_launches; }
 
 void prof_begin(const char* name, cudaStream_t stream) {
-    if (!g_profiling) return;
+    g_open = nullptr;
+    if (!g_profiling.load(std::memory_order_relaxed)) return;
     Timer t{name, nullptr, nullptr};
     if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) return;
     cudaEventRecord(t.start, stream);
+    std::lock_guard<std::mutex> lk(g_mu);
     g_timers.push_back(t);
+    g_open = &g_timers.back();
 }
 
 void prof_end(cudaStream_t stream) {
-    if (!g_profiling || g_timers.empty()) return;
-    cudaEventRecord(g_timers.back().stop, stream);
+    if (!g_open) return;
+    cudaEventRecord(g_open->stop, stream);
+    g_open = nullptr;
 }
 
 }  // namespace nr_internal
@@ -52,10 +60,11 @@ extern "C" const char* nr_b200_error_string(int code) {
 
 extern "C" int nr_b200_last_launch_count(void) { return nr_internal::launch_count(); }
 
-extern "C" void nr_b200_set_profiling(int enabled) { nr_internal::g_profiling = enabled != 0; }
+extern "C" void nr_b200_set_profiling(int enabled) { nr_internal::g_profiling.store(enabled != 0); }
 
 extern "C" int nr_b200_read_profile(char* names, size_t names_bytes, float* ms, int max_entries) {
     using namespace nr_internal;
+    std::lock_guard<std::mutex> lk(g_mu);
     int n = 0;
     size_t off = 0;
     for (Timer& t : g_timers) {
