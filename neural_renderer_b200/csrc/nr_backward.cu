@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "nr_b200.h"
 #include "nr_bbox.cuh"
@@ -31,10 +32,10 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kFaceQueue = 512;               // surviving faces per round (9-bit queue slot in a task word)
-constexpr int kTaskQueue = 16384;             // (face, edge, line) slots expanded per round
-constexpr int kMaxLines = 16;                 // W upper bound: keeps kTaskQueue / (3 W) >= kThreads faces per round
-constexpr int kStripBytes = 64 * 1024;        // shared memory budget for the staged strip
+constexpr int kFaceQueue = 512;               // surviving faces queued per cull round (9-bit slot in a task word)
+constexpr int kTaskCap = 4096;                // (face, edge, line) scan tasks per expansion round (12-bit rank)
+constexpr int kMaxLines = 16;                 // W upper bound (4-bit line in a task word)
+constexpr int kStripBytesDefault = 32 * 1024; // shared memory budget for the staged strip (NR_B200_STRIP_KB overrides)
 
 struct BwdParams {
     const float* faces;
@@ -51,10 +52,17 @@ struct BwdParams {
     float* grad_textures;
     int B, F, S, ts, nchunks;
     int W;          // lines per strip (power of two)
-    int pitch;      // records per staged line (S, +1 padding for axis 0)
+    int len_shift;  // scan length >> len_shift -> one of 32 sort buckets
     uint32_t flags;
     float eps, two_over_S, tex_cmp, tex_val;
 };
+
+// MUFU.RCP (about 1 ulp): the edge-scan terms are held to 1e-4 relative, not to bit-exactness
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 // upstream gradient of raster pixel (row, col) of plane `pl` -- folds the 2x2 average-pooling backward
 __device__ __forceinline__ float load_grad(const float* g, bool aa, int S, size_t img_plane_index, int row, int col) {
@@ -64,18 +72,27 @@ __device__ __forceinline__ float load_grad(const float* g, bool aa, int S, size_
 }
 
 // ------------------------------------------------------------------------------------------------ k_edge_scan
-// record layout (8 words): [I0 I1 I2 g0 | g1 g2 fim galpha]; alpha itself is (fim >= 0)
-template <bool kRGB, bool kALPHA>
+// Shared-memory strip, per pixel (line-major, d1 contiguous):
+//   ag[i] = {A, g0, g1, g2}   A = sum_c I_c * g_c (+ alpha * g_alpha): the scan evaluates the reference's
+//                              diff_grad = sum_c (I_c - ref_c) * g_c as A - sum_c ref_c * g_c (one 16-byte load/visit)
+//   ci[i] = {I0, I1, I2, fim} colours and face index, needed only at task set-up and by the short in-scan
+//   ga[i] = g_alpha            only when both rgb and alpha gradients exist (kMode == 3)
+// kMode: 1 = rgb, 2 = alpha only (stored as g0 = g_alpha, I0 = alpha), 3 = rgb + alpha
+template <int kMode>
 __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ BwdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* rec = reinterpret_cast<float4*>(smem_raw);  // [W][pitch][2]
+    const int S = p.S, W = p.W;
+    float4* ag = reinterpret_cast<float4*>(smem_raw);
+    float4* ci = ag + (size_t)W * S;
+    float* gal = reinterpret_cast<float*>(ci + (size_t)W * S);
     __shared__ int s_faceq[kFaceQueue];
-    __shared__ uint16_t s_taskq[kTaskQueue];
-    __shared__ int s_nface, s_ntask;
+    __shared__ uint32_t s_tmp[kTaskCap];     // unsorted tasks: q<<23 | e<<21 | line<<17 | bucket<<12 | rank
+    __shared__ uint16_t s_sorted[kTaskCap];  // tasks ordered by descending scan length: q<<6 | e<<4 | line
+    __shared__ int s_hist[32], s_off[32];
+    __shared__ int s_nface, s_ntask, s_next;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int axis = blockIdx.y, b = blockIdx.z;
-    const int S = p.S, W = p.W, pitch = p.pitch;
     const int l0 = blockIdx.x * W;
     const int nlines = min(W, S - l0);
     const bool aa = (p.flags & NR_ANTI_ALIASING) != 0;
@@ -88,23 +105,34 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
         else           { line = i / S;      d1 = i % S;      x = d1;        y = l0 + line; }
         const int row = S - 1 - y;
         const size_t o = (size_t)row * S + x;
-        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, 0.f);
         const int fi = __ldg(p.fim + (size_t)b * plane + o);
-        r1.z = __int_as_float(fi);
-        if (kRGB) {
+        float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(fi));
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float alpha = fi >= 0 ? 1.0f : 0.0f;
+        if (kMode == 2) {
+            const float g = load_grad(p.g_alpha, aa, S, (size_t)b, row, x);
+            c.x = alpha;
+            a.y = g;
+            a.x = alpha * g;
+        } else {
             const float* rm = p.rgb + (size_t)b * 3 * plane + o;
-            r0.x = __ldg(rm); r0.y = __ldg(rm + plane); r0.z = __ldg(rm + 2 * plane);
-            if (p.g_rgb) {
-                r0.w = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 0, row, x);
-                r1.x = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 1, row, x);
-                r1.y = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 2, row, x);
+            c.x = __ldg(rm); c.y = __ldg(rm + plane); c.z = __ldg(rm + 2 * plane);
+            a.y = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 0, row, x);
+            a.z = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 1, row, x);
+            a.w = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 2, row, x);
+            float acc = 0.0f;
+            if (kMode == 3) {
+                const float g = load_grad(p.g_alpha, aa, S, (size_t)b, row, x);
+                gal[(size_t)line * S + d1] = g;
+                acc = alpha * g;
             }
+            a.x = __fmaf_rn(c.z, a.w, __fmaf_rn(c.y, a.z, __fmaf_rn(c.x, a.y, acc)));
         }
-        if (kALPHA && p.g_alpha) r1.w = load_grad(p.g_alpha, aa, S, (size_t)b, row, x);
-        rec[((size_t)line * pitch + d1) * 2 + 0] = r0;
-        rec[((size_t)line * pitch + d1) * 2 + 1] = r1;
+        ag[(size_t)line * S + d1] = a;
+        ci[(size_t)line * S + d1] = c;
     }
-    if (tid == 0) { s_nface = 0; s_ntask = 0; }
+    if (tid < 32) s_hist[tid] = 0;
+    if (tid == 0) { s_nface = 0; s_ntask = 0; s_next = 0; }
     __syncthreads();
 
     const uint2* bbox = p.bbox + (size_t)b * p.F;
@@ -112,46 +140,82 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
     const float fS = (float)S;
     const int lhi = l0 + nlines - 1;
 
-    // per-task geometry, recomputed from the face exactly as rasterize.py:545-575 does
-    struct Edge {
-        float p00, p01, p10, p11, p20, p21;
-        int dir, d0_from, d0_to, pi0, pi1;
+    // Geometry of one (face, edge, line) scan, evaluated exactly as rasterize.py:545-609 / :662-672 does.
+    struct Task {
+        float d1_cross, k0, k1;  // dist_v = (d1 - d1_cross) * k_v  (k_v = ratio_v * 2 / S), +-eps
+        bool has0, has1;         // vertex not exactly on this line (rasterize.py:648, :653)
+        int dir, d1_in, d1_out;  // crossing pixel inside / outside the face
+        int out_from, out_to;    // out-scan range (empty unless the inside pixel shows this face)
+        int in_from, in_to;      // in-scan range
+        int pi0, pi1;
+        bool valid;
     };
-    auto edge_setup = [&](int f, int e, Edge& E) {
+    auto task_setup = [&](int f, int e, int line, Task& T) {
         const float* v = p.faces + ((size_t)b * p.F + f) * 9;
         const int pi0 = e, pi1 = (e + 1) % 3, pi2 = (e + 2) % 3;
         const int a = axis, c = 1 - axis;
-        E.p00 = nr::to_pixel(__ldg(v + 3 * pi0 + a), fS); E.p01 = nr::to_pixel(__ldg(v + 3 * pi0 + c), fS);
-        E.p10 = nr::to_pixel(__ldg(v + 3 * pi1 + a), fS); E.p11 = nr::to_pixel(__ldg(v + 3 * pi1 + c), fS);
-        E.p20 = nr::to_pixel(__ldg(v + 3 * pi2 + a), fS); E.p21 = nr::to_pixel(__ldg(v + 3 * pi2 + c), fS);
-        const bool lt = E.p00 < E.p10;
-        E.dir = (axis == 0) ? (lt ? -1 : 1) : (lt ? 1 : -1);
+        const float p00 = nr::to_pixel(__ldg(v + 3 * pi0 + a), fS), p01 = nr::to_pixel(__ldg(v + 3 * pi0 + c), fS);
+        const float p10 = nr::to_pixel(__ldg(v + 3 * pi1 + a), fS), p11 = nr::to_pixel(__ldg(v + 3 * pi1 + c), fS);
+        T.pi0 = pi0; T.pi1 = pi1;
+        T.valid = false;
+        const bool lt = p00 < p10;
+        T.dir = (axis == 0) ? (lt ? -1 : 1) : (lt ? 1 : -1);
         // (int)max(ceil(min(p0,p1)), 0.) and (int)min(max(p0,p1), is - 1.): truncating conversions (NaN -> 0)
-        E.d0_from = __float2int_rz(fmaxf(ceilf(fminf(E.p00, E.p10)), 0.0f));
-        E.d0_to = __float2int_rz(fminf(fmaxf(E.p00, E.p10), (float)(S - 1)));
-        E.pi0 = pi0; E.pi1 = pi1;
+        const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p00, p10)), 0.0f));
+        const int d0_to = __float2int_rz(fminf(fmaxf(p00, p10), (float)(S - 1)));
+        const int d0 = l0 + line;
+        if (d0 < d0_from || d0 > d0_to) return;
+        const float fd0 = (float)d0;
+        const float slope = __fdiv_rn(__fsub_rn(p11, p01), __fsub_rn(p10, p00));
+        T.d1_cross = __fmaf_rn(__fsub_rn(fd0, p00), slope, p01);
+        T.d1_in = __float2int_rz(T.dir > 0 ? floorf(T.d1_cross) : ceilf(T.d1_cross));
+        T.d1_out = T.d1_in + T.dir;
+        if (T.d1_in < 0 || T.d1_in >= S || T.d1_out < 0 || T.d1_out >= S) return;
+        T.valid = true;
+        T.has0 = (p10 != fd0); T.has1 = (p00 != fd0);
+        const float len = __fsub_rn(p10, p00);
+        T.k0 = __fdiv_rn(len, __fsub_rn(p10, fd0)) * p.two_over_S;
+        T.k1 = __fdiv_rn(len, __fsub_rn(fd0, p00)) * p.two_over_S;
+        // out-scan: from the outside pixel to the image border, only if the inside pixel shows this face
+        T.out_from = 0; T.out_to = -1;
+        if (__float_as_int(ci[(size_t)line * S + T.d1_in].w) == f) {
+            const int lim = (T.dir > 0) ? S - 1 : 0;
+            T.out_from = max(min(T.d1_out, lim), 0);
+            T.out_to = min(max(T.d1_out, lim), S - 1);
+        }
+        // in-scan: from the inside pixel to where this line leaves the face through one of the other two edges
+        const float p20 = nr::to_pixel(__ldg(v + 3 * pi2 + a), fS), p21 = nr::to_pixel(__ldg(v + 3 * pi2 + c), fS);
+        float ba, bb, ea, eb;
+        if (__fmul_rn(__fsub_rn(fd0, p00), __fsub_rn(fd0, p20)) < 0.0f) { ba = p00; bb = p01; ea = p20; eb = p21; }
+        else { ba = p20; bb = p21; ea = p10; eb = p11; }
+        const float cross2 = __fmaf_rn(__fsub_rn(fd0, ba), __fdiv_rn(__fsub_rn(eb, bb), __fsub_rn(ea, ba)), bb);
+        const int lim2 = __float2int_rz(T.dir > 0 ? ceilf(cross2) : floorf(cross2));
+        T.in_from = max(min(T.d1_in, lim2), 0);
+        T.in_to = min(max(T.d1_in, lim2), S - 1);
     };
 
-    // faces are queued until the next batch of kThreads could overflow the face queue or the slot expansion
-    static_assert(kTaskQueue / (3 * kMaxLines) >= kThreads && kFaceQueue >= 2 * kThreads, "queue sizing");
-    const int cap_faces = min(kFaceQueue, kTaskQueue / (3 * nlines));
+    const int len_shift = p.len_shift;  // scan length >> len_shift indexes 32 sort buckets
+    // faces are queued until the next batch of kThreads could overflow the face queue or the task expansion
+    const int cap_faces = min(kFaceQueue, kTaskCap / (3 * nlines));
     int nface = 0;  // uniform across the CTA
     for (int base = 0; base < p.F; base += kThreads) {
         // ---- 2a. cull faces against the strip (chunk box, then face box, on the d0 axis only: scans run to the border)
         const int f = base + tid;
+        const bool last = base + kThreads >= p.F;
         bool pass = false;
+        bool chunk_hit;
         {
             const uint2 cb = __ldg(cbox + (base / kChunk));  // kThreads == kChunk: one chunk per iteration
             const uint32_t cv = (axis == 0) ? cb.x : cb.y;
-            const bool chunk_hit = !(unpack_lo(cv) > lhi || unpack_hi(cv) < l0);
+            chunk_hit = !(unpack_lo(cv) > lhi || unpack_hi(cv) < l0);  // uniform across the CTA
             if (chunk_hit && f < p.F) {
                 const uint2 bb = __ldg(bbox + f);
                 const uint32_t v = (axis == 0) ? bb.x : bb.y;
                 pass = (unpack_lo(bb.x) <= unpack_hi(bb.x)) && !(unpack_lo(v) > lhi || unpack_hi(v) < l0);
             }
         }
+        if (!chunk_hit && !(last && nface > 0)) continue;  // whole chunk misses the strip: no barrier needed
         const int cnt = __syncthreads_count(pass);
-        const bool last = base + kThreads >= p.F;
         if (cnt) {
             const uint32_t m = __ballot_sync(0xffffffffu, pass);
             if (m) {
@@ -165,98 +229,112 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
         if (nface == 0 || (!last && nface + kThreads <= cap_faces)) continue;
         __syncthreads();
 
-        // ---- 2b. expand (face, edge, line) slots, keep the ones whose line is inside the edge's span
-        for (int i = tid; i < nface * 3 * nlines; i += kThreads) {
-            const int line = i % nlines, qe = i / nlines;
-            const int e = qe % 3, q = qe / 3;
-            Edge E;
-            edge_setup(s_faceq[q], e, E);
-            const int d0 = l0 + line;
-            if (d0 >= E.d0_from && d0 <= E.d0_to) {
-                const int t = atomicAdd(&s_ntask, 1);
-                s_taskq[t] = (uint16_t)((q << 7) | (e << 5) | line);
+        // the queue may hold more faces than one expansion round can take (cap_faces < kThreads for wide strips)
+        for (int q0 = 0; q0 < nface; q0 += cap_faces) {
+            const int nq = min(cap_faces, nface - q0);
+            // ---- 2b. expand (face, edge, line) slots; valid ones become tasks bucketed by scan length
+            for (int i = tid; i < nq * 3 * nlines; i += kThreads) {
+                const int line = i % nlines, qe = i / nlines;
+                const int e = qe % 3, q = q0 + qe / 3;
+                Task T;
+                task_setup(s_faceq[q], e, line, T);
+                if (T.valid) {
+                    const int L = max(T.out_to - T.out_from + 1, 0) + max(T.in_to - T.in_from + 1, 0);
+                    const int bucket = min(L >> len_shift, 31);
+                    const int rank = atomicAdd(&s_hist[bucket], 1);
+                    const int t = atomicAdd(&s_ntask, 1);
+                    s_tmp[t] = ((uint32_t)q << 23) | ((uint32_t)e << 21) | ((uint32_t)line << 17) | ((uint32_t)bucket << 12) | (uint32_t)rank;
+                }
             }
+            __syncthreads();
+            const int ntask = s_ntask;
+            if (tid < 32) {  // offsets: longest scans first
+                const int h = s_hist[31 - lane];
+                int incl = h;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                s_off[31 - lane] = incl - h;
+            }
+            __syncthreads();
+            for (int t = tid; t < ntask; t += kThreads) {
+                const uint32_t e = s_tmp[t];
+                const int bucket = (e >> 12) & 31, rank = e & 4095;
+                s_sorted[s_off[bucket] + rank] = (uint16_t)(((e >> 23) << 6) | (((e >> 21) & 3) << 4) | ((e >> 17) & 15));
+            }
+            __syncthreads();
+
+            // ---- 3. one scan task per lane, similar lengths side by side
+            for (;;) {
+                int t0 = 0;
+                if (lane == 0) t0 = atomicAdd(&s_next, 32);
+                t0 = __shfl_sync(0xffffffffu, t0, 0);
+                if (t0 >= ntask) break;
+                const int t = t0 + lane;
+                if (t >= ntask) continue;
+                const uint32_t tk = s_sorted[t];
+                const int line = tk & 15, e = (tk >> 4) & 3, q = tk >> 6;
+                const int fn = s_faceq[q];
+                Task T;
+                task_setup(fn, e, line, T);
+                const float4* lag = ag + (size_t)line * S;
+                const float4* lci = ci + (size_t)line * S;
+                const float* lga = gal + (size_t)line * S;
+                float acc0 = 0.0f, acc1 = 0.0f;
+                // vertices lying exactly on the line do not move with it: k = 0, eps = inf  ->  1/dist = 0
+                const float k0 = T.has0 ? T.k0 : 0.0f, k1 = T.has1 ? T.k1 : 0.0f;
+                {   // out-scan (rasterize.py:604-659): reference colour = inside pixel; (d1 - d1_cross) keeps the sign of dir
+                    const float4 cin = lci[T.d1_in];
+                    const float ra = (kMode == 3) ? ((__float_as_int(cin.w) >= 0) ? 1.0f : 0.0f) : 0.0f;
+                    const float fdir = (float)T.dir;
+                    const float e0 = T.has0 ? ((fdir * k0 > 0.0f) ? p.eps : -p.eps) : __int_as_float(0x7f800000);
+                    const float e1 = T.has1 ? ((fdir * k1 > 0.0f) ? p.eps : -p.eps) : __int_as_float(0x7f800000);
+                    for (int d1 = T.out_from; d1 <= T.out_to; d1++) {
+                        const float4 r = lag[d1];
+                        float dg = __fmaf_rn(-cin.z, r.w, __fmaf_rn(-cin.y, r.z, __fmaf_rn(-cin.x, r.y, r.x)));
+                        if (kMode == 3) dg = __fmaf_rn(-ra, lga[d1], dg);
+                        // relu gate of rasterize.py:647 without a branch (NaN diff_grad is not reproduced: max() drops it)
+                        dg = fmaxf(dg, 0.0f);
+                        const float tt = __fsub_rn((float)d1, T.d1_cross);
+                        acc0 = __fmaf_rn(-dg, rcp_approx(__fmaf_rn(tt, k0, e0)), acc0);
+                        acc1 = __fmaf_rn(-dg, rcp_approx(__fmaf_rn(tt, k1, e1)), acc1);
+                    }
+                }
+                {   // in-scan (rasterize.py:662-730): reference colour = outside pixel, only pixels that show this face
+                    const float4 cout = lci[T.d1_out];
+                    const float ra = (kMode == 3) ? ((__float_as_int(cout.w) >= 0) ? 1.0f : 0.0f) : 0.0f;
+                    for (int d1 = T.in_from; d1 <= T.in_to; d1++) {
+                        if (__float_as_int(lci[d1].w) != fn) continue;
+                        const float4 r = lag[d1];
+                        float dg = __fmaf_rn(-cout.z, r.w, __fmaf_rn(-cout.y, r.z, __fmaf_rn(-cout.x, r.y, r.x)));
+                        if (kMode == 3) dg = __fmaf_rn(-ra, lga[d1], dg);
+                        if (dg > 0.0f) {
+                            const float tt = __fsub_rn((float)d1, T.d1_cross);
+                            if (T.has0) {
+                                float dist = tt * T.k0;
+                                dist = (0.0f < dist) ? dist + p.eps : dist - p.eps;
+                                acc0 -= __fdividef(dg, dist);
+                            }
+                            if (T.has1) {
+                                float dist = tt * T.k1;
+                                dist = (0.0f < dist) ? dist + p.eps : dist - p.eps;
+                                acc1 -= __fdividef(dg, dist);
+                            }
+                        }
+                    }
+                }
+                float* gf = p.grad_faces + ((size_t)b * p.F + fn) * 9 + (1 - axis);
+                if (acc0 != 0.0f) atomicAdd(gf + 3 * T.pi0, acc0);
+                if (acc1 != 0.0f) atomicAdd(gf + 3 * T.pi1, acc1);
+            }
+            __syncthreads();
+            if (tid < 32) s_hist[tid] = 0;
+            if (tid == 0) { s_ntask = 0; s_next = 0; }
+            __syncthreads();
         }
-        __syncthreads();
-        const int ntask = s_ntask;
-
-        // ---- 3. one scan task per lane
-        for (int t = tid; t < ntask; t += kThreads) {
-            const uint32_t tk = s_taskq[t];
-            const int line = tk & 31, e = (tk >> 5) & 3, q = tk >> 7;
-            const int fn = s_faceq[q];
-            Edge E;
-            edge_setup(fn, e, E);
-            const int d0 = l0 + line;
-            const float fd0 = (float)d0;
-            const float slope = __fdiv_rn(__fsub_rn(E.p11, E.p01), __fsub_rn(E.p10, E.p00));
-            const float d1_cross = __fmaf_rn(__fsub_rn(fd0, E.p00), slope, E.p01);
-            const int d1_in = __float2int_rz(E.dir > 0 ? floorf(d1_cross) : ceilf(d1_cross));
-            const int d1_out = d1_in + E.dir;
-            if (d1_in < 0 || d1_in >= S || d1_out < 0 || d1_out >= S) continue;
-            const float4* lrec = rec + (size_t)line * pitch * 2;
-            const float4 in0 = lrec[d1_in * 2], in1 = lrec[d1_in * 2 + 1];
-            const float4 out0 = lrec[d1_out * 2], out1 = lrec[d1_out * 2 + 1];
-            const float a_in = (__float_as_int(in1.z) >= 0) ? 1.0f : 0.0f;
-            const float a_out = (__float_as_int(out1.z) >= 0) ? 1.0f : 0.0f;
-            const bool has0 = (E.p10 != fd0), has1 = (E.p00 != fd0);
-            const float len = __fsub_rn(E.p10, E.p00);
-            const float k0 = __fdiv_rn(len, __fsub_rn(E.p10, fd0)) * p.two_over_S;
-            const float k1 = __fdiv_rn(len, __fsub_rn(fd0, E.p00)) * p.two_over_S;
-            float acc0 = 0.0f, acc1 = 0.0f;
-
-            auto visit = [&](int d1, float ra, float r0, float r1, float r2) {
-                // ra / r0..r2: the reference pixel's alpha / colour (in-pixel for the out-scan, out-pixel for the in-scan)
-                const float4 c0 = lrec[d1 * 2], c1 = lrec[d1 * 2 + 1];
-                float dg = 0.0f;
-                if (kALPHA) {
-                    const float a = (__float_as_int(c1.z) >= 0) ? 1.0f : 0.0f;
-                    dg = __fmaf_rn(__fsub_rn(a, ra), c1.w, dg);
-                }
-                if (kRGB) {
-                    dg = __fmaf_rn(__fsub_rn(c0.x, r0), c0.w, dg);
-                    dg = __fmaf_rn(__fsub_rn(c0.y, r1), c1.x, dg);
-                    dg = __fmaf_rn(__fsub_rn(c0.z, r2), c1.y, dg);
-                }
-                if (dg <= 0.0f) return;
-                const float tt = __fsub_rn((float)d1, d1_cross);
-                if (has0) {
-                    float dist = tt * k0;
-                    dist = (0.0f < dist) ? dist + p.eps : dist - p.eps;
-                    acc0 -= __fdividef(dg, dist);
-                }
-                if (has1) {
-                    float dist = tt * k1;
-                    dist = (0.0f < dist) ? dist + p.eps : dist - p.eps;
-                    acc1 -= __fdividef(dg, dist);
-                }
-            };
-
-            // out-scan: only when the inside pixel shows this face (rasterize.py:604-659)
-            if (__float_as_int(in1.z) == fn) {
-                const int lim = (E.dir > 0) ? S - 1 : 0;
-                const int from = max(min(d1_out, lim), 0), to = min(max(d1_out, lim), S - 1);
-                for (int d1 = from; d1 <= to; d1++) visit(d1, a_in, in0.x, in0.y, in0.z);
-            }
-            // in-scan: towards the opposite edge, pixels that show this face (rasterize.py:662-730)
-            {
-                float ba, bb, ea, eb;
-                if (__fmul_rn(__fsub_rn(fd0, E.p00), __fsub_rn(fd0, E.p20)) < 0.0f) { ba = E.p00; bb = E.p01; ea = E.p20; eb = E.p21; }
-                else { ba = E.p20; bb = E.p21; ea = E.p10; eb = E.p11; }
-                const float cross2 = __fmaf_rn(__fsub_rn(fd0, ba), __fdiv_rn(__fsub_rn(eb, bb), __fsub_rn(ea, ba)), bb);
-                const int lim = __float2int_rz(E.dir > 0 ? ceilf(cross2) : floorf(cross2));
-                const int from = max(min(d1_in, lim), 0), to = min(max(d1_in, lim), S - 1);
-                for (int d1 = from; d1 <= to; d1++) {
-                    if (__float_as_int(lrec[d1 * 2 + 1].z) != fn) continue;
-                    visit(d1, a_out, out0.x, out0.y, out0.z);
-                }
-            }
-            float* gf = p.grad_faces + ((size_t)b * p.F + fn) * 9 + (1 - axis);
-            if (acc0 != 0.0f) atomicAdd(gf + 3 * E.pi0, acc0);
-            if (acc1 != 0.0f) atomicAdd(gf + 3 * E.pi1, acc1);
-        }
-        __syncthreads();
-        if (tid == 0) { s_nface = 0; s_ntask = 0; }
+        if (tid == 0) s_nface = 0;
         nface = 0;
         __syncthreads();
     }
@@ -339,12 +417,12 @@ inline float float_le(double d) {
     return f;
 }
 
-template <bool R, bool A>
+template <int kMode>
 int launch_edge_scan(const BwdParams& p, int nstrips, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(k_edge_scan<R, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_edge_scan<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return NR_ERR_CUDA;
     nr_internal::LaunchScope ls("k_edge_scan", stream);
-    k_edge_scan<R, A><<<dim3(nstrips, 2, p.B), kThreads, smem, stream>>>(p);
+    k_edge_scan<kMode><<<dim3(nstrips, 2, p.B), kThreads, smem, stream>>>(p);
     return NR_OK;
 }
 
@@ -401,18 +479,22 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
             k_face_bbox<<<dim3(nchunks, B), kChunk, 0, stream>>>(a->faces, F, S, nchunks, bbox, cbox);
         }
         p.bbox = bbox; p.chunk_bbox = cbox; p.nchunks = nchunks;
+        const bool use_rgb = rgb && p.g_rgb, use_alpha = alpha && p.g_alpha;
+        const int rec_bytes = (use_rgb && use_alpha) ? 36 : 32;
+        size_t strip_bytes = kStripBytesDefault;
+        if (const char* env = getenv("NR_B200_STRIP_KB")) strip_bytes = (size_t)atoi(env) * 1024;  // tuning knob
         int W = kMaxLines;
-        while (W > 1 && (size_t)W * (S + 1) * 32 > (size_t)kStripBytes) W >>= 1;
+        while (W > 1 && (size_t)W * S * rec_bytes > strip_bytes) W >>= 1;
         p.W = W;
-        p.pitch = S + 1;  // +1 record: lines start on different bank groups (transposed stores of axis 0)
-        const size_t smem = (size_t)W * p.pitch * 32;
-        if (smem > 200 * 1024) return NR_ERR_UNSUPPORTED;
+        p.len_shift = 3;
+        while ((2 * S) >> p.len_shift > 32) p.len_shift++;
+        const size_t smem = (size_t)W * S * rec_bytes;
+        if (smem > 160 * 1024) return NR_ERR_UNSUPPORTED;
         const int nstrips = (S + W - 1) / W;
         int rc;
-        const bool use_rgb = rgb && p.g_rgb, use_alpha = alpha && p.g_alpha;
-        if (use_rgb && use_alpha) rc = launch_edge_scan<true, true>(p, nstrips, smem, stream);
-        else if (use_rgb) rc = launch_edge_scan<true, false>(p, nstrips, smem, stream);
-        else rc = launch_edge_scan<false, true>(p, nstrips, smem, stream);
+        if (use_rgb && use_alpha) rc = launch_edge_scan<3>(p, nstrips, smem, stream);
+        else if (use_rgb) rc = launch_edge_scan<1>(p, nstrips, smem, stream);
+        else rc = launch_edge_scan<2>(p, nstrips, smem, stream);
         if (rc != NR_OK) return rc;
     }
     const dim3 pgrid((unsigned)(((size_t)S * S + 255) / 256), B);
