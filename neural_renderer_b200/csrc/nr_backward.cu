@@ -31,11 +31,10 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kFaceQueue = 512;               // surviving faces queued per cull round (9-bit slot in a task word)
-constexpr int kTaskCap = 4096;                // (face, edge, line) scan tasks per expansion round (12-bit rank)
+// k_edge_scan<kMode, kT>: kT threads per CTA; 2*kT queued faces (<= 9-bit slot), 8*kT scan tasks (<= 12-bit rank) per round
+constexpr int kEdgeScanThreadsDefault = 128;
 constexpr int kMaxLines = 16;                 // W upper bound (4-bit line in a task word)
-constexpr int kStripBytesDefault = 32 * 1024; // shared memory budget for the staged strip (NR_B200_STRIP_KB overrides)
+constexpr int kStripBytesDefault = 16 * 1024; // shared memory budget for the staged strip (NR_B200_STRIP_KB overrides)
 
 struct BwdParams {
     const float* faces;
@@ -48,10 +47,14 @@ struct BwdParams {
     const float* g_depth;
     const uint2* bbox;
     const uint2* chunk_bbox;
+    const int* strip_cnt;   // [B*2*(nstrips+1)]  faces per (item, axis, strip); slot nstrips = faces wider than kWideStrips
+    const int* strip_off;   // exclusive prefix of strip_cnt
+    const int* strip_list;  // face indices, grouped by (item, axis, strip)
     float* grad_faces;
     float* grad_textures;
     int B, F, S, ts, nchunks;
     int W;          // lines per strip (power of two)
+    int w_log2, nstrips;
     int len_shift;  // scan length >> len_shift -> one of 32 sort buckets
     uint32_t flags;
     float eps, two_over_S, tex_cmp, tex_val;
@@ -71,6 +74,76 @@ __device__ __forceinline__ float load_grad(const float* g, bool aa, int S, size_
     return 0.25f * __ldg(g + img_plane_index * (size_t)H * H + (size_t)(row >> 1) * H + (col >> 1));
 }
 
+// ------------------------------------------------------------------------------------------------ strip binning
+// Every front face is appended to the list of each strip its pixel box overlaps, per axis (count -> scan -> fill), so a
+// strip CTA reads exactly its faces instead of culling all F boxes.  Faces spanning more than kWideStrips strips go
+// to one "wide" list per (item, axis) that every strip of that item/axis walks with a box test; this bounds the list
+// storage at kWideStrips entries per face and axis.
+constexpr int kWideStrips = 8;
+
+template <bool kFill>
+__global__ void __launch_bounds__(256) k_strip_bin(const uint2* __restrict__ bbox, int F, int w_log2, int nstrips,
+                                                   int* __restrict__ cnt, const int* __restrict__ off,
+                                                   int* __restrict__ cursor, int* __restrict__ list) {
+    const int b = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const uint2 bb = __ldg(bbox + (size_t)b * F + f);
+    if (unpack_lo(bb.x) > unpack_hi(bb.x)) return;  // culled face
+#pragma unroll
+    for (int axis = 0; axis < 2; axis++) {
+        const uint32_t v = axis == 0 ? bb.x : bb.y;
+        const int s_lo = unpack_lo(v) >> w_log2, s_hi = unpack_hi(v) >> w_log2;
+        const size_t base = ((size_t)b * 2 + axis) * (nstrips + 1);
+        if (s_hi - s_lo + 1 > kWideStrips) {
+            if (!kFill) atomicAdd(cnt + base + nstrips, 1);
+            else list[off[base + nstrips] + atomicAdd(cursor + base + nstrips, 1)] = f;
+        } else {
+            for (int st = s_lo; st <= s_hi; st++) {
+                if (!kFill) atomicAdd(cnt + base + st, 1);
+                else list[off[base + st] + atomicAdd(cursor + base + st, 1)] = f;
+            }
+        }
+    }
+}
+
+// exclusive prefix sum of n counters by one CTA (n = B * 2 * (nstrips + 1): a few thousand to ~10^5)
+__global__ void __launch_bounds__(1024) k_strip_scan(const int* __restrict__ cnt, int* __restrict__ off, int n) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n ? cnt[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = warp_sum[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_sum[lane] = wi - w;  // exclusive
+        }
+        __syncthreads();
+        const int c = carry;
+        if (i < n) off[i] = c + warp_sum[warp] + incl - v;
+        __syncthreads();
+        if (tid == 1023) carry = c + warp_sum[warp] + incl;
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ k_edge_scan
 // Shared-memory strip, per pixel (line-major, d1 contiguous):
 //   ag[i] = {A, g0, g1, g2}   A = sum_c I_c * g_c (+ alpha * g_alpha): the scan evaluates the reference's
@@ -78,8 +151,10 @@ __device__ __forceinline__ float load_grad(const float* g, bool aa, int S, size_
 //   ci[i] = {I0, I1, I2, fim} colours and face index, needed only at task set-up and by the short in-scan
 //   ga[i] = g_alpha            only when both rgb and alpha gradients exist (kMode == 3)
 // kMode: 1 = rgb, 2 = alpha only (stored as g0 = g_alpha, I0 = alpha), 3 = rgb + alpha
-template <int kMode>
+template <int kMode, int kThreads>
 __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ BwdParams p) {
+    constexpr int kFaceQueue = 2 * kThreads, kTaskCap = 8 * kThreads;
+    static_assert(kFaceQueue <= 512 && kTaskCap <= 4096, "task word layout");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = p.S, W = p.W;
     float4* ag = reinterpret_cast<float4*>(smem_raw);
@@ -136,7 +211,6 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
     __syncthreads();
 
     const uint2* bbox = p.bbox + (size_t)b * p.F;
-    const uint2* cbox = p.chunk_bbox + (size_t)b * p.nchunks;
     const float fS = (float)S;
     const int lhi = l0 + nlines - 1;
 
@@ -198,23 +272,26 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
     // faces are queued until the next batch of kThreads could overflow the face queue or the task expansion
     const int cap_faces = min(kFaceQueue, kTaskCap / (3 * nlines));
     int nface = 0;  // uniform across the CTA
-    for (int base = 0; base < p.F; base += kThreads) {
-        // ---- 2a. cull faces against the strip (chunk box, then face box, on the d0 axis only: scans run to the border)
-        const int f = base + tid;
-        const bool last = base + kThreads >= p.F;
+    const size_t cid = ((size_t)b * 2 + axis) * (p.nstrips + 1);
+    const int n_own = __ldg(p.strip_cnt + cid + blockIdx.x), n_wide = __ldg(p.strip_cnt + cid + p.nstrips);
+    const int* own = p.strip_list + __ldg(p.strip_off + cid + blockIdx.x);
+    const int* wide = p.strip_list + __ldg(p.strip_off + cid + p.nstrips);
+    const int ncand = n_own + n_wide;
+    for (int base = 0; base < ncand; base += kThreads) {
+        // ---- 2a. this strip's faces (binned by k_strip_bin) plus the item's wide faces that overlap it
+        const int i = base + tid;
+        const bool last = base + kThreads >= ncand;
         bool pass = false;
-        bool chunk_hit;
-        {
-            const uint2 cb = __ldg(cbox + (base / kChunk));  // kThreads == kChunk: one chunk per iteration
-            const uint32_t cv = (axis == 0) ? cb.x : cb.y;
-            chunk_hit = !(unpack_lo(cv) > lhi || unpack_hi(cv) < l0);  // uniform across the CTA
-            if (chunk_hit && f < p.F) {
-                const uint2 bb = __ldg(bbox + f);
-                const uint32_t v = (axis == 0) ? bb.x : bb.y;
-                pass = (unpack_lo(bb.x) <= unpack_hi(bb.x)) && !(unpack_lo(v) > lhi || unpack_hi(v) < l0);
-            }
+        int f = 0;
+        if (i < n_own) {
+            f = __ldg(own + i);
+            pass = true;
+        } else if (i < ncand) {
+            f = __ldg(wide + (i - n_own));
+            const uint2 bb = __ldg(bbox + f);
+            const uint32_t v = (axis == 0) ? bb.x : bb.y;
+            pass = !(unpack_lo(v) > lhi || unpack_hi(v) < l0);
         }
-        if (!chunk_hit && !(last && nface > 0)) continue;  // whole chunk misses the strip: no barrier needed
         const int cnt = __syncthreads_count(pass);
         if (cnt) {
             const uint32_t m = __ballot_sync(0xffffffffu, pass);
@@ -417,20 +494,56 @@ inline float float_le(double d) {
     return f;
 }
 
-template <int kMode>
-int launch_edge_scan(const BwdParams& p, int nstrips, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(k_edge_scan<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int kMode, int kT>
+int launch_edge_scan_t(const BwdParams& p, int nstrips, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(k_edge_scan<kMode, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return NR_ERR_CUDA;
     nr_internal::LaunchScope ls("k_edge_scan", stream);
-    k_edge_scan<kMode><<<dim3(nstrips, 2, p.B), kThreads, smem, stream>>>(p);
+    k_edge_scan<kMode, kT><<<dim3(nstrips, 2, p.B), kT, smem, stream>>>(p);
     return NR_OK;
+}
+
+template <int kMode>
+int launch_edge_scan(const BwdParams& p, int nstrips, size_t smem, cudaStream_t stream) {
+    int threads = kEdgeScanThreadsDefault;
+    if (const char* env = getenv("NR_B200_ES_THREADS")) threads = atoi(env);  // tuning knob
+    if (threads == 256) return launch_edge_scan_t<kMode, 256>(p, nstrips, smem, stream);
+    return launch_edge_scan_t<kMode, 128>(p, nstrips, smem, stream);
 }
 
 }  // namespace
 
+namespace {
+struct BinLayout {
+    int W, w_log2, nstrips;
+    size_t ncounters, off_cnt, off_off, off_cursor, off_list, total;
+};
+// strip width from the shared-memory budget; workspace = boxes | counters | offsets | cursors | lists
+BinLayout bin_layout(int B, int F, int S, int rec_bytes) {
+    BinLayout L{};
+    size_t strip_bytes = kStripBytesDefault;
+    if (const char* env = getenv("NR_B200_STRIP_KB")) strip_bytes = (size_t)atoi(env) * 1024;  // tuning knob
+    int W = kMaxLines;
+    while (W > 1 && (size_t)W * S * rec_bytes > strip_bytes) W >>= 1;
+    L.W = W;
+    L.w_log2 = 0;
+    while ((1 << L.w_log2) < W) L.w_log2++;
+    L.nstrips = (S + W - 1) / W;
+    L.ncounters = (size_t)B * 2 * (L.nstrips + 1);
+    L.off_cnt = bbox_workspace_bytes(B, F);
+    L.off_off = L.off_cnt + nr_align_up(L.ncounters * sizeof(int), 256);
+    L.off_cursor = L.off_off + nr_align_up(L.ncounters * sizeof(int), 256);
+    L.off_list = L.off_cursor + nr_align_up(L.ncounters * sizeof(int), 256);
+    L.total = L.off_list + nr_align_up((size_t)B * F * 2 * kWideStrips * sizeof(int), 256);
+    return L;
+}
+}  // namespace
+
 extern "C" size_t nr_b200_backward_workspace_bytes(int32_t B, int32_t F, int32_t S, int32_t ts, uint32_t flags) {
-    (void)S; (void)ts; (void)flags;
-    return bbox_workspace_bytes(B, F);
+    (void)ts;
+    if (B <= 0 || F <= 0 || S <= 0) return 16;
+    const bool both = (flags & NR_RETURN_RGB) && (flags & NR_RETURN_ALPHA);
+    return bin_layout(B, F, S, both ? 36 : 32).total;
 }
 
 extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_stream) {
@@ -481,16 +594,36 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
         p.bbox = bbox; p.chunk_bbox = cbox; p.nchunks = nchunks;
         const bool use_rgb = rgb && p.g_rgb, use_alpha = alpha && p.g_alpha;
         const int rec_bytes = (use_rgb && use_alpha) ? 36 : 32;
-        size_t strip_bytes = kStripBytesDefault;
-        if (const char* env = getenv("NR_B200_STRIP_KB")) strip_bytes = (size_t)atoi(env) * 1024;  // tuning knob
-        int W = kMaxLines;
-        while (W > 1 && (size_t)W * S * rec_bytes > strip_bytes) W >>= 1;
-        p.W = W;
+        const BinLayout L = bin_layout(B, F, S, (rgb && alpha) ? 36 : 32);  // same strip width as the workspace query
+        const int W = L.W;
+        p.W = W; p.w_log2 = L.w_log2; p.nstrips = L.nstrips;
         p.len_shift = 3;
         while ((2 * S) >> p.len_shift > 32) p.len_shift++;
         const size_t smem = (size_t)W * S * rec_bytes;
         if (smem > 160 * 1024) return NR_ERR_UNSUPPORTED;
-        const int nstrips = (S + W - 1) / W;
+        const int nstrips = L.nstrips;
+        char* wsb = (char*)a->workspace;
+        int* cnt = (int*)(wsb + L.off_cnt);
+        int* off = (int*)(wsb + L.off_off);
+        int* cursor = (int*)(wsb + L.off_cursor);
+        int* list = (int*)(wsb + L.off_list);
+        if (cudaMemsetAsync(cnt, 0, L.off_list - L.off_cnt, stream) != cudaSuccess) return NR_ERR_CUDA;  // counters, offsets, cursors
+        {
+            const dim3 g((F + 255) / 256, B);
+            {
+                nr_internal::LaunchScope ls("k_strip_bin", stream);
+                k_strip_bin<false><<<g, 256, 0, stream>>>(bbox, F, L.w_log2, nstrips, cnt, nullptr, nullptr, nullptr);
+            }
+            {
+                nr_internal::LaunchScope ls("k_strip_scan", stream);
+                k_strip_scan<<<1, 1024, 0, stream>>>(cnt, off, (int)L.ncounters);
+            }
+            {
+                nr_internal::LaunchScope ls("k_strip_bin", stream);
+                k_strip_bin<true><<<g, 256, 0, stream>>>(bbox, F, L.w_log2, nstrips, cnt, off, cursor, list);
+            }
+        }
+        p.strip_cnt = cnt; p.strip_off = off; p.strip_list = list;
         int rc;
         if (use_rgb && use_alpha) rc = launch_edge_scan<3>(p, nstrips, smem, stream);
         else if (use_rgb) rc = launch_edge_scan<1>(p, nstrips, smem, stream);
