@@ -67,6 +67,14 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
+// vector float reductions (no return value): one L2 request for 2 / 4 consecutive, naturally aligned floats
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // upstream gradient of raster pixel (row, col) of plane `pl` -- folds the 2x2 average-pooling backward
 __device__ __forceinline__ float load_grad(const float* g, bool aa, int S, size_t img_plane_index, int row, int col) {
     if (!aa) return __ldg(g + img_plane_index * (size_t)S * S + (size_t)row * S + col);
@@ -438,13 +446,20 @@ __global__ void __launch_bounds__(256) k_texture_grad(const __grid_constant__ Bw
     const int ts = p.ts;
     const nr::TexCoord tc = nr::texture_coords(w, zp, __ldg(v + 2), __ldg(v + 5), __ldg(v + 8), ts, p.tex_cmp, p.tex_val);
     float* gt = p.grad_textures + ((size_t)b * p.F + fn) * (size_t)(ts * ts * ts) * 3;
+    // The two corners that differ only along texture axis 2 are neighbours in memory: 6 consecutive floats per
+    // corner pair.  They are scattered with the widest vector reductions their alignment allows
+    // (red.global.add.v4/v2.f32, sm_90+): 2-4 requests per pair instead of 6 scalar ones.
 #pragma unroll
-    for (int pn = 0; pn < 8; pn++) {
-        const float cw = nr::corner_weight(tc, pn);
-        float* t = gt + nr::corner_index(tc, pn, ts) * 3;
-        atomicAdd(t + 0, cw * g0);
-        atomicAdd(t + 1, cw * g1);
-        atomicAdd(t + 2, cw * g2);
+    for (int pr = 0; pr < 4; pr++) {
+        const float w_lo = nr::corner_weight(tc, pr), w_hi = nr::corner_weight(tc, pr | 4);
+        float* t = gt + nr::corner_index(tc, pr, ts) * 3;
+        const float v0 = w_lo * g0, v1 = w_lo * g1, v2 = w_lo * g2, v3 = w_hi * g0, v4 = w_hi * g1, v5 = w_hi * g2;
+        switch ((reinterpret_cast<uintptr_t>(t) >> 2) & 3) {
+            case 0: red_add_v4(t, v0, v1, v2, v3); red_add_v2(t + 4, v4, v5); break;
+            case 2: red_add_v2(t, v0, v1); red_add_v4(t + 2, v2, v3, v4, v5); break;
+            case 3: atomicAdd(t, v0); red_add_v4(t + 1, v1, v2, v3, v4); atomicAdd(t + 5, v5); break;
+            default: atomicAdd(t, v0); red_add_v2(t + 1, v1, v2); red_add_v2(t + 3, v3, v4); atomicAdd(t + 5, v5); break;
+        }
     }
 }
 
