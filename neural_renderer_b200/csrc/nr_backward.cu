@@ -153,21 +153,31 @@ __global__ void __launch_bounds__(1024) k_strip_scan(const int* __restrict__ cnt
 }
 
 // ------------------------------------------------------------------------------------------------ k_edge_scan
-// Shared-memory strip, per pixel (line-major, d1 contiguous):
-//   ag[i] = {A, g0, g1, g2}   A = sum_c I_c * g_c (+ alpha * g_alpha): the scan evaluates the reference's
-//                              diff_grad = sum_c (I_c - ref_c) * g_c as A - sum_c ref_c * g_c (one 16-byte load/visit)
-//   ci[i] = {I0, I1, I2, fim} colours and face index, needed only at task set-up and by the short in-scan
-//   ga[i] = g_alpha            only when both rgb and alpha gradients exist (kMode == 3)
-// kMode: 1 = rgb, 2 = alpha only (stored as g0 = g_alpha, I0 = alpha), 3 = rgb + alpha
+// packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): two pixels of a scan advance per instruction
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// Shared-memory strip.  Pixels of a line are stored as PAIRS (2*pp, 2*pp+1) so that one 16-byte load feeds one packed
+// multiply-add:
+//   P[pp] = {A_e, A_o, g0_e, g0_o}   A = sum_c I_c * g_c (+ alpha * g_alpha): the scan evaluates the reference's
+//   Q[pp] = {g1_e, g1_o, g2_e, g2_o}     diff_grad = sum_c (I_c - ref_c) * g_c  as  A - sum_c ref_c * g_c
+//   R[pp] = {ga_e, ga_o}             only when both rgb and alpha gradients exist (kMode == 3)
+//   ci[i] = {I0, I1, I2, fim}        colours and face index per pixel: task set-up and the short in-scan only
+// kMode: 1 = rgb, 2 = alpha only (g0 = g_alpha, I0 = alpha), 3 = rgb + alpha
 template <int kMode, int kThreads>
 __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ BwdParams p) {
     constexpr int kFaceQueue = 2 * kThreads, kTaskCap = 8 * kThreads;
     static_assert(kFaceQueue <= 512 && kTaskCap <= 4096, "task word layout");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = p.S, W = p.W;
-    float4* ag = reinterpret_cast<float4*>(smem_raw);
-    float4* ci = ag + (size_t)W * S;
-    float* gal = reinterpret_cast<float*>(ci + (size_t)W * S);
+    const int Sp = (S + 1) & ~1, npair = Sp >> 1;
+    float4* P = reinterpret_cast<float4*>(smem_raw);
+    float4* Q = P + (size_t)W * npair;
+    float4* ci = Q + (size_t)W * npair;
+    float2* R = reinterpret_cast<float2*>(ci + (size_t)W * Sp);
     __shared__ int s_faceq[kFaceQueue];
     __shared__ uint32_t s_tmp[kTaskCap];     // unsorted tasks: q<<23 | e<<21 | line<<17 | bucket<<12 | rank
     __shared__ uint16_t s_sorted[kTaskCap];  // tasks ordered by descending scan length: q<<6 | e<<4 | line
@@ -182,37 +192,47 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
     const size_t plane = (size_t)S * S;
 
     // ---- 1. stage the strip (image orientation in global memory: raster row y is stored at row S-1-y)
-    for (int i = tid; i < nlines * S; i += kThreads) {
-        int line, d1, x, y;
-        if (axis == 0) { line = i % nlines; d1 = i / nlines; x = l0 + line; y = d1; }   // columns: d0 = x, d1 = y
-        else           { line = i / S;      d1 = i % S;      x = d1;        y = l0 + line; }
-        const int row = S - 1 - y;
-        const size_t o = (size_t)row * S + x;
-        const int fi = __ldg(p.fim + (size_t)b * plane + o);
-        float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(fi));
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float alpha = fi >= 0 ? 1.0f : 0.0f;
-        if (kMode == 2) {
-            const float g = load_grad(p.g_alpha, aa, S, (size_t)b, row, x);
-            c.x = alpha;
-            a.y = g;
-            a.x = alpha * g;
-        } else {
-            const float* rm = p.rgb + (size_t)b * 3 * plane + o;
-            c.x = __ldg(rm); c.y = __ldg(rm + plane); c.z = __ldg(rm + 2 * plane);
-            a.y = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 0, row, x);
-            a.z = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 1, row, x);
-            a.w = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 2, row, x);
-            float acc = 0.0f;
-            if (kMode == 3) {
-                const float g = load_grad(p.g_alpha, aa, S, (size_t)b, row, x);
-                gal[(size_t)line * S + d1] = g;
-                acc = alpha * g;
+    for (int i = tid; i < nlines * Sp; i += kThreads) {
+        int line, d1;
+        if (axis == 0) { line = i % nlines; d1 = i / nlines; }   // columns: d0 = x, d1 = y
+        else           { line = i / Sp;     d1 = i % Sp; }
+        float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        float A = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f, ga = 0.f;
+        if (d1 < S) {  // (the padding pixel of an odd raster size stays zero)
+            const int x = (axis == 0) ? l0 + line : d1, y = (axis == 0) ? d1 : l0 + line;
+            const int row = S - 1 - y;
+            const size_t o = (size_t)row * S + x;
+            const int fi = __ldg(p.fim + (size_t)b * plane + o);
+            c.w = __int_as_float(fi);
+            const float alpha = fi >= 0 ? 1.0f : 0.0f;
+            if (kMode == 2) {
+                g0 = load_grad(p.g_alpha, aa, S, (size_t)b, row, x);
+                c.x = alpha;
+                A = alpha * g0;
+            } else {
+                const float* rm = p.rgb + (size_t)b * 3 * plane + o;
+                c.x = __ldg(rm); c.y = __ldg(rm + plane); c.z = __ldg(rm + 2 * plane);
+                g0 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 0, row, x);
+                g1 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 1, row, x);
+                g2 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 2, row, x);
+                float acc = 0.0f;
+                if (kMode == 3) {
+                    ga = load_grad(p.g_alpha, aa, S, (size_t)b, row, x);
+                    acc = alpha * ga;
+                }
+                A = __fmaf_rn(c.z, g2, __fmaf_rn(c.y, g1, __fmaf_rn(c.x, g0, acc)));
             }
-            a.x = __fmaf_rn(c.z, a.w, __fmaf_rn(c.y, a.z, __fmaf_rn(c.x, a.y, acc)));
         }
-        ag[(size_t)line * S + d1] = a;
-        ci[(size_t)line * S + d1] = c;
+        const size_t pi = (size_t)line * npair + (d1 >> 1);
+        const int h = d1 & 1;
+        reinterpret_cast<float*>(P + pi)[h] = A;
+        reinterpret_cast<float*>(P + pi)[2 + h] = g0;
+        if (kMode != 2) {
+            reinterpret_cast<float*>(Q + pi)[h] = g1;
+            reinterpret_cast<float*>(Q + pi)[2 + h] = g2;
+        }
+        if (kMode == 3) reinterpret_cast<float*>(R + pi)[h] = ga;
+        ci[(size_t)line * Sp + d1] = c;
     }
     if (tid < 32) s_hist[tid] = 0;
     if (tid == 0) { s_nface = 0; s_ntask = 0; s_next = 0; }
@@ -236,17 +256,18 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
         const float* v = p.faces + ((size_t)b * p.F + f) * 9;
         const int pi0 = e, pi1 = (e + 1) % 3, pi2 = (e + 2) % 3;
         const int a = axis, c = 1 - axis;
-        const float p00 = nr::to_pixel(__ldg(v + 3 * pi0 + a), fS), p01 = nr::to_pixel(__ldg(v + 3 * pi0 + c), fS);
-        const float p10 = nr::to_pixel(__ldg(v + 3 * pi1 + a), fS), p11 = nr::to_pixel(__ldg(v + 3 * pi1 + c), fS);
         T.pi0 = pi0; T.pi1 = pi1;
         T.valid = false;
-        const bool lt = p00 < p10;
-        T.dir = (axis == 0) ? (lt ? -1 : 1) : (lt ? 1 : -1);
+        T.out_from = 0; T.out_to = -1; T.in_from = 0; T.in_to = -1;
+        const float p00 = nr::to_pixel(__ldg(v + 3 * pi0 + a), fS), p10 = nr::to_pixel(__ldg(v + 3 * pi1 + a), fS);
         // (int)max(ceil(min(p0,p1)), 0.) and (int)min(max(p0,p1), is - 1.): truncating conversions (NaN -> 0)
         const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p00, p10)), 0.0f));
         const int d0_to = __float2int_rz(fminf(fmaxf(p00, p10), (float)(S - 1)));
         const int d0 = l0 + line;
-        if (d0 < d0_from || d0 > d0_to) return;
+        if (d0 < d0_from || d0 > d0_to) return;  // most (face, edge, line) slots end here
+        const float p01 = nr::to_pixel(__ldg(v + 3 * pi0 + c), fS), p11 = nr::to_pixel(__ldg(v + 3 * pi1 + c), fS);
+        const bool lt = p00 < p10;
+        T.dir = (axis == 0) ? (lt ? -1 : 1) : (lt ? 1 : -1);
         const float fd0 = (float)d0;
         const float slope = __fdiv_rn(__fsub_rn(p11, p01), __fsub_rn(p10, p00));
         T.d1_cross = __fmaf_rn(__fsub_rn(fd0, p00), slope, p01);
@@ -259,8 +280,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
         T.k0 = __fdiv_rn(len, __fsub_rn(p10, fd0)) * p.two_over_S;
         T.k1 = __fdiv_rn(len, __fsub_rn(fd0, p00)) * p.two_over_S;
         // out-scan: from the outside pixel to the image border, only if the inside pixel shows this face
-        T.out_from = 0; T.out_to = -1;
-        if (__float_as_int(ci[(size_t)line * S + T.d1_in].w) == f) {
+        if (__float_as_int(ci[(size_t)line * Sp + T.d1_in].w) == f) {
             const int lim = (T.dir > 0) ? S - 1 : 0;
             T.out_from = max(min(T.d1_out, lim), 0);
             T.out_to = min(max(T.d1_out, lim), S - 1);
@@ -274,6 +294,30 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
         const int lim2 = __float2int_rz(T.dir > 0 ? ceilf(cross2) : floorf(cross2));
         T.in_from = max(min(T.d1_in, lim2), 0);
         T.in_to = min(max(T.d1_in, lim2), S - 1);
+    };
+    // scalar visit (in-scan, and out-scans of the rare tasks with a vertex exactly on the line)
+    auto visit = [&](const Task& T, int line, int d1, float r0, float r1, float r2, float ra, float& acc0, float& acc1) {
+        const size_t pi = (size_t)line * npair + (d1 >> 1);
+        const int h = d1 & 1;
+        float dg = reinterpret_cast<const float*>(P + pi)[h];
+        dg = __fmaf_rn(-r0, reinterpret_cast<const float*>(P + pi)[2 + h], dg);
+        if (kMode != 2) {
+            dg = __fmaf_rn(-r1, reinterpret_cast<const float*>(Q + pi)[h], dg);
+            dg = __fmaf_rn(-r2, reinterpret_cast<const float*>(Q + pi)[2 + h], dg);
+        }
+        if (kMode == 3) dg = __fmaf_rn(-ra, reinterpret_cast<const float*>(R + pi)[h], dg);
+        if (!(dg > 0.0f)) return;
+        const float tt = __fsub_rn((float)d1, T.d1_cross);
+        if (T.has0) {
+            float dist = tt * T.k0;
+            dist = (0.0f < dist) ? dist + p.eps : dist - p.eps;
+            acc0 -= __fdividef(dg, dist);
+        }
+        if (T.has1) {
+            float dist = tt * T.k1;
+            dist = (0.0f < dist) ? dist + p.eps : dist - p.eps;
+            acc1 -= __fdividef(dg, dist);
+        }
     };
 
     const int len_shift = p.len_shift;  // scan length >> len_shift indexes 32 sort buckets
@@ -324,7 +368,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
                 Task T;
                 task_setup(s_faceq[q], e, line, T);
                 if (T.valid) {
-                    const int L = max(T.out_to - T.out_from + 1, 0) + max(T.in_to - T.in_from + 1, 0);
+                    const int L = max(T.out_to - T.out_from + 1, 0) + 2 * max(T.in_to - T.in_from + 1, 0);
                     const int bucket = min(L >> len_shift, 31);
                     const int rank = atomicAdd(&s_hist[bucket], 1);
                     const int t = atomicAdd(&s_ntask, 1);
@@ -351,68 +395,114 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
             }
             __syncthreads();
 
-            // ---- 3. one scan task per lane, similar lengths side by side
+            // ---- 3. warps pull batches of 32 tasks of similar length.  Every lane sets up its own task and runs the
+            //         short in-scan; the long out-scans are then swept by 8 lanes per task (4 tasks at a time), two
+            //         pixels per lane and step, with conflict-free 16-byte shared-memory loads.
             for (;;) {
                 int t0 = 0;
                 if (lane == 0) t0 = atomicAdd(&s_next, 32);
                 t0 = __shfl_sync(0xffffffffu, t0, 0);
                 if (t0 >= ntask) break;
                 const int t = t0 + lane;
-                if (t >= ntask) continue;
-                const uint32_t tk = s_sorted[t];
-                const int line = tk & 15, e = (tk >> 4) & 3, q = tk >> 6;
-                const int fn = s_faceq[q];
                 Task T;
-                task_setup(fn, e, line, T);
-                const float4* lag = ag + (size_t)line * S;
-                const float4* lci = ci + (size_t)line * S;
-                const float* lga = gal + (size_t)line * S;
-                float acc0 = 0.0f, acc1 = 0.0f;
-                // vertices lying exactly on the line do not move with it: k = 0, eps = inf  ->  1/dist = 0
-                const float k0 = T.has0 ? T.k0 : 0.0f, k1 = T.has1 ? T.k1 : 0.0f;
-                {   // out-scan (rasterize.py:604-659): reference colour = inside pixel; (d1 - d1_cross) keeps the sign of dir
-                    const float4 cin = lci[T.d1_in];
-                    const float ra = (kMode == 3) ? ((__float_as_int(cin.w) >= 0) ? 1.0f : 0.0f) : 0.0f;
-                    const float fdir = (float)T.dir;
-                    const float e0 = T.has0 ? ((fdir * k0 > 0.0f) ? p.eps : -p.eps) : __int_as_float(0x7f800000);
-                    const float e1 = T.has1 ? ((fdir * k1 > 0.0f) ? p.eps : -p.eps) : __int_as_float(0x7f800000);
-                    for (int d1 = T.out_from; d1 <= T.out_to; d1++) {
-                        const float4 r = lag[d1];
-                        float dg = __fmaf_rn(-cin.z, r.w, __fmaf_rn(-cin.y, r.z, __fmaf_rn(-cin.x, r.y, r.x)));
-                        if (kMode == 3) dg = __fmaf_rn(-ra, lga[d1], dg);
-                        // relu gate of rasterize.py:647 without a branch (NaN diff_grad is not reproduced: max() drops it)
-                        dg = fmaxf(dg, 0.0f);
-                        const float tt = __fsub_rn((float)d1, T.d1_cross);
-                        acc0 = __fmaf_rn(-dg, rcp_approx(__fmaf_rn(tt, k0, e0)), acc0);
-                        acc1 = __fmaf_rn(-dg, rcp_approx(__fmaf_rn(tt, k1, e1)), acc1);
-                    }
+                T.valid = false; T.out_from = 0; T.out_to = -1; T.in_from = 0; T.in_to = -1;
+                T.d1_cross = 0.f; T.k0 = 0.f; T.k1 = 0.f; T.has0 = T.has1 = true; T.dir = 1; T.d1_in = T.d1_out = 0; T.pi0 = T.pi1 = 0;
+                int line = 0, fn = 0;
+                if (t < ntask) {
+                    const uint32_t tk = s_sorted[t];
+                    line = tk & 15;
+                    fn = s_faceq[tk >> 6];
+                    task_setup(fn, (tk >> 4) & 3, line, T);
                 }
-                {   // in-scan (rasterize.py:662-730): reference colour = outside pixel, only pixels that show this face
-                    const float4 cout = lci[T.d1_out];
-                    const float ra = (kMode == 3) ? ((__float_as_int(cout.w) >= 0) ? 1.0f : 0.0f) : 0.0f;
-                    for (int d1 = T.in_from; d1 <= T.in_to; d1++) {
-                        if (__float_as_int(lci[d1].w) != fn) continue;
-                        const float4 r = lag[d1];
-                        float dg = __fmaf_rn(-cout.z, r.w, __fmaf_rn(-cout.y, r.z, __fmaf_rn(-cout.x, r.y, r.x)));
-                        if (kMode == 3) dg = __fmaf_rn(-ra, lga[d1], dg);
-                        if (dg > 0.0f) {
-                            const float tt = __fsub_rn((float)d1, T.d1_cross);
-                            if (T.has0) {
-                                float dist = tt * T.k0;
-                                dist = (0.0f < dist) ? dist + p.eps : dist - p.eps;
-                                acc0 -= __fdividef(dg, dist);
-                            }
-                            if (T.has1) {
-                                float dist = tt * T.k1;
-                                dist = (0.0f < dist) ? dist + p.eps : dist - p.eps;
-                                acc1 -= __fdividef(dg, dist);
-                            }
+                float acc0 = 0.0f, acc1 = 0.0f;  // this lane's own (scalar) contributions
+                float c0 = 0.f, c1 = 0.f, c2 = 0.f, ca = 0.f;
+                bool fast = false;
+                if (T.valid) {
+                    const float4* lci = ci + (size_t)line * Sp;
+                    {   // in-scan (rasterize.py:662-730): reference colour = outside pixel, only pixels that show this face
+                        const float4 cout = lci[T.d1_out];
+                        const float ra = (kMode == 3) ? ((__float_as_int(cout.w) >= 0) ? 1.0f : 0.0f) : 0.0f;
+                        for (int d1 = T.in_from; d1 <= T.in_to; d1++) {
+                            if (__float_as_int(lci[d1].w) != fn) continue;
+                            visit(T, line, d1, cout.x, cout.y, cout.z, ra, acc0, acc1);
                         }
                     }
+                    // out-scan (rasterize.py:604-659): reference colour = inside pixel
+                    const float4 cin = lci[T.d1_in];
+                    c0 = cin.x; c1 = cin.y; c2 = cin.z;
+                    ca = (kMode == 3) ? ((__float_as_int(cin.w) >= 0) ? 1.0f : 0.0f) : 0.0f;
+                    fast = T.has0 && T.has1;
+                    if (!fast)
+                        for (int d1 = T.out_from; d1 <= T.out_to; d1++) visit(T, line, d1, c0, c1, c2, ca, acc0, acc1);
                 }
-                float* gf = p.grad_faces + ((size_t)b * p.F + fn) * 9 + (1 - axis);
-                if (acc0 != 0.0f) atomicAdd(gf + 3 * T.pi0, acc0);
-                if (acc1 != 0.0f) atomicAdd(gf + 3 * T.pi1, acc1);
+                // along an out-scan (d1 - d1_cross) keeps the sign of dir, so the sign of eps is fixed per vertex
+                const float fdir = (float)T.dir;
+                const float e0 = (fdir * T.k0 > 0.0f) ? p.eps : -p.eps, e1 = (fdir * T.k1 > 0.0f) ? p.eps : -p.eps;
+                const int my_from = fast ? T.out_from : 1, my_to = fast ? T.out_to : 0;
+                float* gfb = p.grad_faces + ((size_t)b * p.F + fn) * 9 + (1 - axis);
+                const int qd = lane >> 3, j = lane & 7;
+#pragma unroll 1
+                for (int sub = 0; sub < 8; sub++) {
+                    const int src = sub * 4 + qd;
+                    const int o_from = __shfl_sync(0xffffffffu, my_from, src), o_to = __shfl_sync(0xffffffffu, my_to, src);
+                    const int o_line = __shfl_sync(0xffffffffu, line, src);
+                    const float o_dc = __shfl_sync(0xffffffffu, T.d1_cross, src);
+                    const float o_k0 = __shfl_sync(0xffffffffu, T.k0, src), o_k1 = __shfl_sync(0xffffffffu, T.k1, src);
+                    const float o_e0 = __shfl_sync(0xffffffffu, e0, src), o_e1 = __shfl_sync(0xffffffffu, e1, src);
+                    const float o_c0 = __shfl_sync(0xffffffffu, c0, src), o_c1 = __shfl_sync(0xffffffffu, c1, src);
+                    const float o_c2 = __shfl_sync(0xffffffffu, c2, src);
+                    const float o_ca = (kMode == 3) ? __shfl_sync(0xffffffffu, ca, src) : 0.0f;
+                    if (!__any_sync(0xffffffffu, o_from <= o_to)) continue;
+                    f32x2 a0 = pk(0.f, 0.f), a1 = pk(0.f, 0.f);
+                    if (o_from <= o_to) {
+                        const f32x2 nc0 = pk(-o_c0, -o_c0), nc1 = pk(-o_c1, -o_c1), nc2 = pk(-o_c2, -o_c2), nca = pk(-o_ca, -o_ca);
+                        const f32x2 k0_2 = pk(o_k0, o_k0), k1_2 = pk(o_k1, o_k1), e0_2 = pk(o_e0, o_e0), e1_2 = pk(o_e1, o_e1);
+                        const size_t lb = (size_t)o_line * npair;
+                        const int pb = o_to >> 1;
+                        for (int pp = (o_from >> 1) + j; pp <= pb; pp += 8) {
+                            const float4 pv = P[lb + pp];
+                            f32x2 dg2 = fma2(nc0, pk(pv.z, pv.w), pk(pv.x, pv.y));
+                            if (kMode != 2) {
+                                const float4 qv = Q[lb + pp];
+                                dg2 = fma2(nc1, pk(qv.x, qv.y), dg2);
+                                dg2 = fma2(nc2, pk(qv.z, qv.w), dg2);
+                            }
+                            if (kMode == 3) {
+                                const float2 rv = R[lb + pp];
+                                dg2 = fma2(nca, pk(rv.x, rv.y), dg2);
+                            }
+                            float dga, dgb;
+                            upk(dg2, dga, dgb);
+                            const int y0 = pp << 1;
+                            // relu gate of rasterize.py:647 (max drops a NaN diff_grad) and the ends of the scan range
+                            dga = (y0 >= o_from) ? fmaxf(dga, 0.0f) : 0.0f;
+                            dgb = (y0 + 1 <= o_to) ? fmaxf(dgb, 0.0f) : 0.0f;
+                            const float ta = __fsub_rn((float)y0, o_dc);
+                            const f32x2 tt2 = pk(ta, ta + 1.0f);
+                            const f32x2 d0_2 = fma2(tt2, k0_2, e0_2), d1_2 = fma2(tt2, k1_2, e1_2);
+                            float pa, pb2;
+                            upk(mul2(d0_2, d1_2), pa, pb2);
+                            // one reciprocal serves both vertices: dg / d0 = dg * d1 / (d0 * d1)
+                            const f32x2 t2 = mul2(pk(-dga, -dgb), pk(rcp_approx(pa), rcp_approx(pb2)));
+                            a0 = fma2(t2, d1_2, a0);
+                            a1 = fma2(t2, d0_2, a1);
+                        }
+                    }
+                    float s0a, s0b, s1a, s1b;
+                    upk(a0, s0a, s0b);
+                    upk(a1, s1a, s1b);
+                    float s0 = s0a + s0b, s1 = s1a + s1b;
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    }
+                    // hand the totals to the lane that owns the task
+                    const float r0 = __shfl_sync(0xffffffffu, s0, (lane & 3) << 3), r1 = __shfl_sync(0xffffffffu, s1, (lane & 3) << 3);
+                    if ((lane >> 2) == sub) { acc0 += r0; acc1 += r1; }
+                }
+                if (acc0 != 0.0f) atomicAdd(gfb + 3 * T.pi0, acc0);
+                if (acc1 != 0.0f) atomicAdd(gfb + 3 * T.pi1, acc1);
             }
             __syncthreads();
             if (tid < 32) s_hist[tid] = 0;
@@ -539,7 +629,7 @@ BinLayout bin_layout(int B, int F, int S, int rec_bytes) {
     size_t strip_bytes = kStripBytesDefault;
     if (const char* env = getenv("NR_B200_STRIP_KB")) strip_bytes = (size_t)atoi(env) * 1024;  // tuning knob
     int W = kMaxLines;
-    while (W > 1 && (size_t)W * S * rec_bytes > strip_bytes) W >>= 1;
+    while (W > 1 && (size_t)W * ((S + 1) & ~1) * rec_bytes > strip_bytes) W >>= 1;
     L.W = W;
     L.w_log2 = 0;
     while ((1 << L.w_log2) < W) L.w_log2++;
@@ -614,7 +704,7 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
         p.W = W; p.w_log2 = L.w_log2; p.nstrips = L.nstrips;
         p.len_shift = 3;
         while ((2 * S) >> p.len_shift > 32) p.len_shift++;
-        const size_t smem = (size_t)W * S * rec_bytes;
+        const size_t smem = (size_t)W * ((S + 1) & ~1) * rec_bytes;
         if (smem > 160 * 1024) return NR_ERR_UNSUPPORTED;
         const int nstrips = L.nstrips;
         char* wsb = (char*)a->workspace;
