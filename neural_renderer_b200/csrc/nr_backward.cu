@@ -362,12 +362,19 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
         for (int q0 = 0; q0 < nface; q0 += cap_faces) {
             const int nq = min(cap_faces, nface - q0);
             // ---- 2b. expand (face, edge, line) slots; valid ones become tasks bucketed by scan length
-            for (int i = tid; i < nq * 3 * nlines; i += kThreads) {
-                const int line = i % nlines, qe = i / nlines;
-                const int e = qe % 3, q = q0 + qe / 3;
-                Task T;
-                task_setup(s_faceq[q], e, line, T);
-                if (T.valid) {
+            for (int i = tid; i < nq * 3; i += kThreads) {
+                const int e = i % 3, q = q0 + i / 3;
+                const int f = s_faceq[q];
+                // lines of the strip that this edge spans (same truncating conversions as task_setup)
+                const float* v = p.faces + ((size_t)b * p.F + f) * 9;
+                const float p00 = nr::to_pixel(__ldg(v + 3 * e + axis), fS), p10 = nr::to_pixel(__ldg(v + 3 * ((e + 1) % 3) + axis), fS);
+                const int lo = max(__float2int_rz(fmaxf(ceilf(fminf(p00, p10)), 0.0f)), l0);
+                const int hi = min(__float2int_rz(fminf(fmaxf(p00, p10), (float)(S - 1))), lhi);
+                for (int d0 = lo; d0 <= hi; d0++) {
+                    const int line = d0 - l0;
+                    Task T;
+                    task_setup(f, e, line, T);
+                    if (!T.valid) continue;
                     const int L = max(T.out_to - T.out_from + 1, 0) + 2 * max(T.in_to - T.in_from + 1, 0);
                     const int bucket = min(L >> len_shift, 31);
                     const int rank = atomicAdd(&s_hist[bucket], 1);
@@ -396,8 +403,8 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
             __syncthreads();
 
             // ---- 3. warps pull batches of 32 tasks of similar length.  Every lane sets up its own task and runs the
-            //         short in-scan; the long out-scans are then swept by 8 lanes per task (4 tasks at a time), two
-            //         pixels per lane and step, with conflict-free 16-byte shared-memory loads.
+            //         short in-scan; the long out-scans are then swept by 4 lanes per task (8 tasks at a time), two
+            //         pixels per lane and step (packed f32x2 math, 16-byte shared-memory loads).
             for (;;) {
                 int t0 = 0;
                 if (lane == 0) t0 = atomicAdd(&s_next, 32);
@@ -440,10 +447,10 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
                 const float e0 = (fdir * T.k0 > 0.0f) ? p.eps : -p.eps, e1 = (fdir * T.k1 > 0.0f) ? p.eps : -p.eps;
                 const int my_from = fast ? T.out_from : 1, my_to = fast ? T.out_to : 0;
                 float* gfb = p.grad_faces + ((size_t)b * p.F + fn) * 9 + (1 - axis);
-                const int qd = lane >> 3, j = lane & 7;
+                const int qd = lane >> 2, j = lane & 3;  // 8 tasks per pass, 4 lanes (8 pixels per step) each
 #pragma unroll 1
-                for (int sub = 0; sub < 8; sub++) {
-                    const int src = sub * 4 + qd;
+                for (int sub = 0; sub < 4; sub++) {
+                    const int src = sub * 8 + qd;
                     const int o_from = __shfl_sync(0xffffffffu, my_from, src), o_to = __shfl_sync(0xffffffffu, my_to, src);
                     const int o_line = __shfl_sync(0xffffffffu, line, src);
                     const float o_dc = __shfl_sync(0xffffffffu, T.d1_cross, src);
@@ -459,7 +466,11 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
                         const f32x2 k0_2 = pk(o_k0, o_k0), k1_2 = pk(o_k1, o_k1), e0_2 = pk(o_e0, o_e0), e1_2 = pk(o_e1, o_e1);
                         const size_t lb = (size_t)o_line * npair;
                         const int pb = o_to >> 1;
-                        for (int pp = (o_from >> 1) + j; pp <= pb; pp += 8) {
+                        int pp = (o_from >> 1) + j;
+                        const float ta = __fsub_rn((float)(pp << 1), o_dc);
+                        f32x2 tt2 = pk(ta, ta + 1.0f);  // (d1 - d1_cross) of the lane's two pixels; +8 per step
+                        const f32x2 step2 = pk(8.0f, 8.0f), one2 = pk(1.0f, 1.0f);
+                        for (; pp <= pb; pp += 4) {
                             const float4 pv = P[lb + pp];
                             f32x2 dg2 = fma2(nc0, pk(pv.z, pv.w), pk(pv.x, pv.y));
                             if (kMode != 2) {
@@ -477,9 +488,8 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
                             // relu gate of rasterize.py:647 (max drops a NaN diff_grad) and the ends of the scan range
                             dga = (y0 >= o_from) ? fmaxf(dga, 0.0f) : 0.0f;
                             dgb = (y0 + 1 <= o_to) ? fmaxf(dgb, 0.0f) : 0.0f;
-                            const float ta = __fsub_rn((float)y0, o_dc);
-                            const f32x2 tt2 = pk(ta, ta + 1.0f);
                             const f32x2 d0_2 = fma2(tt2, k0_2, e0_2), d1_2 = fma2(tt2, k1_2, e1_2);
+                            tt2 = fma2(step2, one2, tt2);
                             float pa, pb2;
                             upk(mul2(d0_2, d1_2), pa, pb2);
                             // one reciprocal serves both vertices: dg / d0 = dg * d1 / (d0 * d1)
@@ -493,13 +503,13 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
                     upk(a1, s1a, s1b);
                     float s0 = s0a + s0b, s1 = s1a + s1b;
 #pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) {
+                    for (int o = 1; o < 4; o <<= 1) {
                         s0 += __shfl_xor_sync(0xffffffffu, s0, o);
                         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                     }
                     // hand the totals to the lane that owns the task
-                    const float r0 = __shfl_sync(0xffffffffu, s0, (lane & 3) << 3), r1 = __shfl_sync(0xffffffffu, s1, (lane & 3) << 3);
-                    if ((lane >> 2) == sub) { acc0 += r0; acc1 += r1; }
+                    const float r0 = __shfl_sync(0xffffffffu, s0, (lane & 7) << 2), r1 = __shfl_sync(0xffffffffu, s1, (lane & 7) << 2);
+                    if ((lane >> 3) == sub) { acc0 += r0; acc1 += r1; }
                 }
                 if (acc0 != 0.0f) atomicAdd(gfb + 3 * T.pi0, acc0);
                 if (acc1 != 0.0f) atomicAdd(gfb + 3 * T.pi1, acc1);
