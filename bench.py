@@ -337,8 +337,10 @@ def main():
         out["roofline_fwd"] = dict(roof(fwd_bytes, fwd_ms + kern.get("k_face_bbox", 0.0) / 2), kernel="k_raster_tile",
                                    note="forward rasterize = k_face_bbox + k_raster_tile, 391.5 MB algorithmic")
 
-        # reference's own kernels on this GPU (the reported baseline of BASELINE.md section 2)
+        # reference's own kernels on this GPU (the reported baseline of BASELINE.md section 2); N = 1 only
         try:
+            if world > 1:
+                raise RuntimeError("reported at N=1 only")
             import refhost
             if refhost.available(S, F, ts, w["near"], w["far"], w["eps"], 1, 0, 0):
                 fr, tr = faces.detach(), tex.detach()
@@ -352,8 +354,10 @@ def main():
         except Exception as e:  # pragma: no cover
             out["reference_gpu"] = {"unavailable": repr(e)[:200]}
 
-        # CPU oracle (port) on a bounded sample of the same workload
+        # CPU oracle (port) on a bounded sample of the same workload; N = 1 only (torchrun pins OMP threads to 1)
         try:
+            if world > 1:
+                raise RuntimeError("reported at N=1 only")
             import nr_oracle as o
             nb = max(1, min(B, args.cpu_sample))
             fn, tn, gn = faces_h[:nb].numpy(), tex_h[:nb].numpy(), grad_h[:nb].numpy()
