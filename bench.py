@@ -42,11 +42,7 @@ WORKLOAD = dict(batch_per_gpu=64, num_faces=5000, image_size=256, texture_size=4
                 near=0.1, far=100, eps=1e-4, background=(0.0, 0.0, 0.0))
 
 
-def shard_range(n_items, rank, world):
-    """Contiguous batch shard [lo, hi) of rank `rank` (batch axis shards embarrassingly)."""
-    per = (n_items + world - 1) // world
-    lo = min(n_items, rank * per)
-    return lo, min(n_items, lo + per)
+from neural_renderer_b200.distributed import shard_range  # noqa: E402,F401  (re-exported for the tests)
 
 
 def algorithmic_bytes(B, F, S, ts):
@@ -170,6 +166,61 @@ def oracle_cpu_step(faces_np, tex_np, grad_np):
     return loss, gf, gt
 
 
+def shared_mesh_workload(args, world, rank, local_rank):
+    """BASELINE.json configs[4] shape: ONE shared mesh rendered from many viewpoints, viewpoints sharded over the
+    ranks, vertex / texture gradients summed across ranks with NCCL (the only collective this path has)."""
+    import neural_renderer_b200 as nr
+    from neural_renderer_b200 import synthetic
+    from neural_renderer_b200.distributed import allreduce_shared_grads
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+    barrier = (lambda: dist.barrier(device_ids=[local_rank])) if distributed else (lambda: None)
+    F, S, ts, V = args.shared_faces, args.shared_image, 2, args.views_per_gpu
+    v_np, f_np = synthetic.sphere_mesh(F)
+    vertices = torch.from_numpy((v_np * 0.55).astype(np.float32)).to(dev).requires_grad_(True)   # shared parameters
+    textures = torch.rand((F, ts, ts, ts, 3), generator=torch.Generator().manual_seed(7)).to(dev).requires_grad_(True)
+    faces_idx = torch.from_numpy(f_np).to(dev)
+    lo, hi = shard_range(world * V, rank, world)
+    az = torch.arange(lo, hi, dtype=torch.float32) * (360.0 / (world * V))
+    eyes = nr.get_points_from_angles(torch.full_like(az, 2.732), torch.full_like(az, 30.0), az).to(dev)
+    renderer = nr.Renderer()
+    renderer.image_size, renderer.anti_aliasing, renderer.fill_back = S, False, False
+    renderer.eye = eyes
+    grad = torch.randn((V, 3, S, S), generator=torch.Generator().manual_seed(99 + rank)).to(dev)
+
+    def step():
+        vertices.grad = None
+        textures.grad = None
+        img = renderer.render(vertices[None].expand(V, -1, -1), faces_idx[None].expand(V, -1, -1),
+                              textures[None].expand(V, -1, -1, -1, -1, -1))
+        (img * grad).sum().backward()
+        for w in allreduce_shared_grads([vertices, textures], async_op=True):
+            w.wait()
+
+    ms, t0, t1 = timed_loop(step, args.steps, args.warmup, barrier)
+    if distributed:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * V * S * S * args.steps / (ms * 1e-3) / 1e6
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Mpixels/s fwd+bwd, shared mesh, viewpoint-sharded", "value": round(value, 2), "unit": "Mpixels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "ours",
+            "config": {"workload": "shared mesh: Renderer.render fwd+bwd, %d faces, %dx%d, ts=%d, %d views/GPU, sum "
+                                   "all-reduce of vertex (%.1f MB) and texture (%.1f MB) gradients"
+                                   % (F, S, S, ts, V, vertices.numel() * 4 / 1e6, textures.numel() * 4 / 1e6),
+                       "collective": "nccl all_reduce(sum) x2 per step" if distributed else "none (1 rank)"}}))
+    if distributed:
+        dist.destroy_process_group()
+
+
 def timed_loop(step, steps, warmup, barrier):
     """W warm-up steps, then exactly K steps bracketed by barrier + synchronize, timed with CUDA events on the
     current stream."""
@@ -198,6 +249,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=64, help="batch items of the workload timed on the CPU oracle")
     ap.add_argument("--no-side-measurements", action="store_true", help="skip cpu_baseline / reference_gpu / kernels")
+    ap.add_argument("--workload", default="headline", choices=["headline", "shared_mesh"])
+    ap.add_argument("--shared-faces", type=int, default=1000000)
+    ap.add_argument("--shared-image", type=int, default=1024)
+    ap.add_argument("--views-per-gpu", type=int, default=8)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -211,6 +266,8 @@ def main():
 
     if args.impl == "reference":
         return reference_arm(args, world, rank, local_rank)
+    if args.workload == "shared_mesh":
+        return shared_mesh_workload(args, world, rank, local_rank)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA GPU: this package has no CPU path")

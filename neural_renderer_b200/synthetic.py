@@ -32,16 +32,13 @@ def sphere_mesh(num_faces=5000):
     st, ct = np.sin(theta)[:, None], np.cos(theta)[:, None]
     v = np.stack([st * np.cos(phi)[None, :], ct * np.ones_like(phi)[None, :], st * np.sin(phi)[None, :]], axis=-1)
     vertices = v.reshape(-1, 3)
-    faces = []
-    for i in range(n_lat):
-        for j in range(n_lon):
-            a = i * n_lon + j
-            b = (i + 1) * n_lon + j
-            c = (i + 1) * n_lon + (j + 1) % n_lon
-            d = i * n_lon + (j + 1) % n_lon
-            faces.append((a, b, c))
-            faces.append((a, c, d))
-    faces = np.array(faces[:num_faces], dtype=np.int32)
+    i, j = np.meshgrid(np.arange(n_lat), np.arange(n_lon), indexing="ij")
+    a = i * n_lon + j
+    b = (i + 1) * n_lon + j
+    c = (i + 1) * n_lon + (j + 1) % n_lon
+    d = i * n_lon + (j + 1) % n_lon
+    faces = np.stack([np.stack([a, b, c], axis=-1), np.stack([a, c, d], axis=-1)], axis=2).reshape(-1, 3)
+    faces = np.ascontiguousarray(faces[:num_faces], dtype=np.int32)
     assert faces.shape[0] == num_faces
     return vertices, faces
 

@@ -51,8 +51,12 @@ def _shard_worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = bench.shard_range(10, rank, world)
     # shared-mesh gradient reduction used by config 5: sum over viewpoint shards
-    g = torch.full((4,), float(hi - lo))
-    dist.all_reduce(g)
+    from neural_renderer_b200.distributed import allreduce_shared_grads
+    param = torch.zeros(4, requires_grad=True)
+    param.grad = torch.full((4,), float(hi - lo))
+    for w in allreduce_shared_grads([param], async_op=True):
+        w.wait()
+    g = param.grad
     t = torch.tensor([1.0 + rank])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     out.put((rank, lo, hi, g.tolist(), float(t)))
