@@ -33,8 +33,11 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTilePix = 4096;
-constexpr int kRing = 64;      // per-warp ring of survivor records
-constexpr int kRecWords = 20;  // inv[9] z[3] | x0 y0 x1 y1 | x2 y2 fn box
+constexpr int kRing = 32;      // per-warp ring of survivors being swept: x0 y0 x1 y1 | x2 y2 fnrec box
+constexpr int kRingWords = 8;
+constexpr int kTab = 512;      // per-tile table of survivor records {inv[9], z[3]} that fragments and the shade pass share
+constexpr int kTabWords = 12;
+constexpr uint32_t kNoRec = 1023;  // z-keys carry (face index << 10 | table slot); 1023 = "not in the table"
 
 struct FwdParams {
     const float* faces;
@@ -59,41 +62,58 @@ struct FwdParams {
 
 // ---------------------------------------------------------------------------------------------- k_raster_tile
 struct __align__(16) TileShared {
-    unsigned long long zbuf[kTilePix];        // 32 KB  (ordered zp bits << 32 | face index), ~0 = empty
-    float ring[kWarps][kRing][kRecWords];     // 40 KB  per-warp survivor records
-    uint32_t fq[kWarps][64];                  //  2 KB  per-warp fragment ring: slot << 12 | pixel-in-tile
+    unsigned long long zbuf[kTilePix];        // 32 KB  (ordered zp bits << 32 | face index << 10 | table slot), ~0 = empty
+    float tab[kTab][kTabWords];               // 24 KB  survivor records {inv[9], z0, z1, z2} of this tile
+    float ring[kWarps][kRing][kRingWords];    //  8 KB  per-warp sweep records
+    uint32_t fq[kWarps][64];                  //  2 KB  per-warp fragment ring: ring slot << 12 | pixel-in-tile
     float xp[64];
     float yp[64];
     int next_group;
+    int tab_count;
 };
+
+// {inv[9], z[3]} of face fn of batch item b, straight from global memory (survivors beyond the table's capacity)
+__device__ __forceinline__ void face_record(const FwdParams& p, int b, int fn, float inv[9], float z[3]) {
+    const float* v = p.faces + ((size_t)b * p.F + fn) * 9;
+    float c[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) c[k] = __ldg(v + k);
+    const float fS = (float)p.S;
+    nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS), nr::to_pixel(c[4], fS),
+                     nr::to_pixel(c[6], fS), nr::to_pixel(c[7], fS), inv);
+    z[0] = c[2]; z[1] = c[5]; z[2] = c[8];
+}
 
 struct Shaded {
     int fim;
     float w0, w1, w2, depth, r, g, b, alpha;
 };
 
-__device__ __forceinline__ Shaded shade_pixel(const FwdParams& p, int b, unsigned long long key, int xi, int yi,
-                                              float bgr, float bgg, float bgb) {
+__device__ __forceinline__ Shaded shade_pixel(const FwdParams& p, const float (*tab)[kTabWords], int b,
+                                              unsigned long long key, int xi, int yi, float bgr, float bgg, float bgb) {
     Shaded o;
     if (key == ~0ull) {
         o.fim = -1; o.w0 = o.w1 = o.w2 = 0.0f; o.depth = p.far_val; o.r = bgr; o.g = bgg; o.b = bgb; o.alpha = 0.0f;
         return o;
     }
-    const int fn = (int)(uint32_t)(key & 0xFFFFFFFFull);
+    const uint32_t fnrec = (uint32_t)(key & 0xFFFFFFFFull);
+    const int fn = (int)(fnrec >> 10);
+    const uint32_t rec = fnrec & 1023u;
     const float zp = nr::ordered_to_float((uint32_t)(key >> 32));
-    const float* v = p.faces + ((size_t)b * p.F + fn) * 9;
-    float c[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) c[k] = __ldg(v + k);
-    const float fS = (float)p.S;
-    float inv[9], w[3];
-    nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS), nr::to_pixel(c[4], fS),
-                     nr::to_pixel(c[6], fS), nr::to_pixel(c[7], fS), inv);
-    (void)nr::weights_and_depth(inv, (float)xi, (float)yi, c[2], c[5], c[8], w);
+    float inv[9], z[3], w[3];
+    if (rec != kNoRec) {
+        const float4* t4 = reinterpret_cast<const float4*>(tab[rec]);
+        const float4 a = t4[0], bb = t4[1], cc = t4[2];
+        inv[0] = a.x; inv[1] = a.y; inv[2] = a.z; inv[3] = a.w; inv[4] = bb.x; inv[5] = bb.y; inv[6] = bb.z; inv[7] = bb.w;
+        inv[8] = cc.x; z[0] = cc.y; z[1] = cc.z; z[2] = cc.w;
+    } else {
+        face_record(p, b, fn, inv, z);
+    }
+    (void)nr::weights_and_depth(inv, (float)xi, (float)yi, z[0], z[1], z[2], w);
     o.fim = fn; o.w0 = w[0]; o.w1 = w[1]; o.w2 = w[2]; o.depth = zp; o.alpha = 1.0f;
     o.r = o.g = o.b = 0.0f;
     if (p.flags & NR_RETURN_RGB) {
-        float z0 = c[2], z1 = c[5], z2 = c[8];
+        float z0 = z[0], z1 = z[1], z2 = z[2];
         if (p.flags & NR_TEX_Z_BATCH0) {  // rasterize.py:389 -- vertex depths of batch item 0
             const float* v0 = p.faces + (size_t)fn * 9;
             z0 = __ldg(v0 + 2); z1 = __ldg(v0 + 5); z2 = __ldg(v0 + 8);
@@ -135,7 +155,7 @@ __global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant_
         sm.xp[tid] = (float)((double)(2 * (tx0 + tid) + 1 - p.S) / dS);
         sm.yp[tid] = (float)((double)(2 * (ty0 + tid) + 1 - p.S) / dS);
     }
-    if (tid == 0) sm.next_group = 0;
+    if (tid == 0) { sm.next_group = 0; sm.tab_count = 0; }
     __syncthreads();
 
     // ------------------------------------------------------------------ raster phase (warp-autonomous)
@@ -143,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant_
         const int ngroups = (p.F + 31) >> 5;
         const uint2* bbox = p.bbox + (size_t)b * p.F;
         const uint2* cbox = p.chunk_bbox + (size_t)b * p.nchunks;
-        float(*ring)[kRecWords] = sm.ring[warp];
+        float(*ring)[kRingWords] = sm.ring[warp];
         uint32_t* fq = sm.fq[warp];
         unsigned long long* zbuf = sm.zbuf;
         const float fS = (float)p.S;
@@ -154,16 +174,23 @@ __global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant_
             if (lane < cnt) {
                 const uint32_t e = fq[(fq_head + lane) & 63];
                 const int slot = (int)(e >> 12), pix = (int)(e & 4095u);
-                const float4* r4 = reinterpret_cast<const float4*>(ring[slot]);
-                const float4 a = r4[0], bb = r4[1], cc = r4[2];
-                const int fn = __float_as_int(ring[slot][18]);
-                const float inv[9] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w, cc.x};
+                const uint32_t fnrec = __float_as_uint(ring[slot][6]);
+                const uint32_t rec = fnrec & 1023u;
+                float inv[9], z[3];
+                if (rec != kNoRec) {
+                    const float4* t4 = reinterpret_cast<const float4*>(sm.tab[rec]);
+                    const float4 a = t4[0], bb = t4[1], cc = t4[2];
+                    inv[0] = a.x; inv[1] = a.y; inv[2] = a.z; inv[3] = a.w; inv[4] = bb.x; inv[5] = bb.y; inv[6] = bb.z; inv[7] = bb.w;
+                    inv[8] = cc.x; z[0] = cc.y; z[1] = cc.z; z[2] = cc.w;
+                } else {
+                    face_record(p, b, (int)(fnrec >> 10), inv, z);  // tile with more than kTab survivors
+                }
                 const int lx = pix & (tw - 1), ly = pix >> p.tw_log2;
                 float w[3];
-                const float zp = nr::weights_and_depth(inv, (float)(tx0 + lx), (float)(ty0 + ly), cc.y, cc.z, cc.w, w);
+                const float zp = nr::weights_and_depth(inv, (float)(tx0 + lx), (float)(ty0 + ly), z[0], z[1], z[2], w);
                 // rasterize.py:331 + :334 against the initial depth_min = far; NaN fails both (never wins)
                 if (zp > p.near_lo && zp < p.far_cmp) {
-                    const unsigned long long key = ((unsigned long long)nr::float_to_ordered(zp) << 32) | (uint32_t)fn;
+                    const unsigned long long key = ((unsigned long long)nr::float_to_ordered(zp) << 32) | fnrec;
                     unsigned long long* addr = zbuf + pix;
                     if (key < *reinterpret_cast<volatile unsigned long long*>(addr)) atomicMin(addr, key);
                 }
@@ -194,49 +221,67 @@ __global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant_
             const uint32_t m = __ballot_sync(0xffffffffu, pass);
             if (m == 0u) continue;
             const int nsurv = __popc(m);
-            // records of faces that still have queued fragments must not be overwritten
+            // sweep records of faces that still have queued fragments must not be overwritten (fragments are queued in
+            // record order, so the oldest one sits at the head of the queue)
             if (fq_n > 0) {
                 const int oldest = (int)(fq[fq_head] >> 12);
-                // live records = distance from the oldest pending fragment's slot to the head, in [1, kRing]
                 if ((((ring_head - oldest - 1) & (kRing - 1)) + 1) + nsurv > kRing) drain(fq_n);
             }
+            int tbase = 0;
+            if (lane == 0) tbase = atomicAdd(&sm.tab_count, nsurv);
+            tbase = __shfl_sync(0xffffffffu, tbase, 0);
             if (pass) {
-                const int slot = (ring_head + __popc(m & lt_mask)) & (kRing - 1);
+                const int rank = __popc(m & lt_mask);
+                const int slot = (ring_head + rank) & (kRing - 1);
+                const int trec = tbase + rank;
+                const uint32_t rec = trec < kTab ? (uint32_t)trec : kNoRec;
                 const float* v = p.faces + ((size_t)b * p.F + f) * 9;
                 float c[9];
 #pragma unroll
                 for (int k = 0; k < 9; k++) c[k] = __ldg(v + k);
-                float inv[9];
-                nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS),
-                                 nr::to_pixel(c[4], fS), nr::to_pixel(c[6], fS), nr::to_pixel(c[7], fS), inv);
+                if (rec != kNoRec) {
+                    float inv[9];
+                    nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS),
+                                     nr::to_pixel(c[4], fS), nr::to_pixel(c[6], fS), nr::to_pixel(c[7], fS), inv);
+                    float4* t4 = reinterpret_cast<float4*>(sm.tab[rec]);
+                    t4[0] = make_float4(inv[0], inv[1], inv[2], inv[3]);
+                    t4[1] = make_float4(inv[4], inv[5], inv[6], inv[7]);
+                    t4[2] = make_float4(inv[8], c[2], c[5], c[8]);
+                }
                 float4* r4 = reinterpret_cast<float4*>(ring[slot]);
-                r4[0] = make_float4(inv[0], inv[1], inv[2], inv[3]);
-                r4[1] = make_float4(inv[4], inv[5], inv[6], inv[7]);
-                r4[2] = make_float4(inv[8], c[2], c[5], c[8]);
-                r4[3] = make_float4(c[0], c[1], c[3], c[4]);
+                r4[0] = make_float4(c[0], c[1], c[3], c[4]);
                 const uint32_t box = (uint32_t)(bx0 - tx0) | ((uint32_t)(bx1 - tx0) << 8) | ((uint32_t)(by0 - ty0) << 16) |
                                      ((uint32_t)(by1 - ty0) << 24);
-                r4[4] = make_float4(c[6], c[7], __int_as_float(f), __uint_as_float(box));
+                r4[1] = make_float4(c[6], c[7], __uint_as_float(((uint32_t)f << 10) | rec), __uint_as_float(box));
             }
             __syncwarp();
             for (int j = 0; j < nsurv; j++) {
                 const int slot = (ring_head + j) & (kRing - 1);
                 const float4* r4 = reinterpret_cast<const float4*>(ring[slot]);
-                const float4 q0 = r4[3], q1 = r4[4];
+                const float4 q0 = r4[0], q1 = r4[1];
                 const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y;
                 const uint32_t box = __float_as_uint(q1.w);
                 const int lx0 = box & 0xFF, lx1 = (box >> 8) & 0xFF, ly0 = (box >> 16) & 0xFF, ly1 = box >> 24;
                 const float dx10 = __fsub_rn(x1, x0), dy10 = __fsub_rn(y1, y0), dx21 = __fsub_rn(x2, x1),
                             dy21 = __fsub_rn(y2, y1), dx02 = __fsub_rn(x0, x2), dy02 = __fsub_rn(y0, y2);
+                const uint32_t slot_bits = (uint32_t)slot << 12;
                 for (int oy = ly0; oy <= ly1; oy += 4) {
                     const int ly = oy + (lane >> 3);
-                    for (int ox = lx0; ox <= lx1; ox += 8) {
-                        const int lx = ox + (lane & 7);
-                        bool in = (lx <= lx1) && (ly <= ly1);
-                        if (in) in = nr::inside_face(sm.xp[lx], sm.yp[ly], x0, y0, x1, y1, x2, y2, dx10, dy10, dx21, dy21, dx02, dy02);
+                    // the row terms of the three edge functions do not change along a row of 8x4 blocks
+                    const float yp = sm.yp[min(ly, 63)];
+                    const float r0 = __fmul_rn(__fsub_rn(yp, y0), dx10), r1 = __fmul_rn(__fsub_rn(yp, y1), dx21),
+                                r2 = __fmul_rn(__fsub_rn(yp, y2), dx02);
+                    const bool row_ok = ly <= ly1;
+                    const uint32_t pix_row = (uint32_t)(ly << p.tw_log2);
+                    for (int lx = lx0 + (lane & 7); __any_sync(0xffffffffu, lx <= lx1); lx += 8) {
+                        const float xp = sm.xp[lx & 63];
+                        const int o0 = r0 < __fmul_rn(__fsub_rn(xp, x0), dy10);
+                        const int o1 = r1 < __fmul_rn(__fsub_rn(xp, x1), dy21);
+                        const int o2 = r2 < __fmul_rn(__fsub_rn(xp, x2), dy02);
+                        const bool in = row_ok && (lx <= lx1) && ((o0 | o1 | o2) == 0);
                         const uint32_t mi = __ballot_sync(0xffffffffu, in);
                         if (mi == 0u) continue;
-                        if (in) fq[(fq_head + fq_n + __popc(mi & lt_mask)) & 63] = ((uint32_t)slot << 12) | (uint32_t)((ly << p.tw_log2) + lx);
+                        if (in) fq[(fq_head + fq_n + __popc(mi & lt_mask)) & 63] = slot_bits | (pix_row + (uint32_t)lx);
                         fq_n += __popc(mi);
                         __syncwarp();
                         if (fq_n >= 32) drain(32);
@@ -262,7 +307,7 @@ __global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant_
             const int lx = pix & (tw - 1), ly = pix >> p.tw_log2;
             const int xi = tx0 + lx, yi = ty0 + ly;
             if (xi >= S || yi >= S) continue;
-            const Shaded s = shade_pixel(p, b, sm.zbuf[pix], xi, yi, bgr, bgg, bgb);
+            const Shaded s = shade_pixel(p, sm.tab, b, sm.zbuf[pix], xi, yi, bgr, bgg, bgb);
             const size_t o = (size_t)b * plane + (size_t)(S - 1 - yi) * S + xi;  // image orientation
             p.fim[o] = s.fim;
             p.dmap[o] = s.depth;
@@ -284,10 +329,10 @@ __global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant_
             const int xi = tx0 + lx, yi = ty0 + ly;
             if (xi >= S || yi >= S) continue;  // S is even: quads are entirely in or out
             // image-orientation quad: top row = raster row yi+1
-            const Shaded tl = shade_pixel(p, b, sm.zbuf[((ly + 1) << p.tw_log2) + lx], xi, yi + 1, bgr, bgg, bgb);
-            const Shaded tr = shade_pixel(p, b, sm.zbuf[((ly + 1) << p.tw_log2) + lx + 1], xi + 1, yi + 1, bgr, bgg, bgb);
-            const Shaded bl = shade_pixel(p, b, sm.zbuf[(ly << p.tw_log2) + lx], xi, yi, bgr, bgg, bgb);
-            const Shaded br = shade_pixel(p, b, sm.zbuf[(ly << p.tw_log2) + lx + 1], xi + 1, yi, bgr, bgg, bgb);
+            const Shaded tl = shade_pixel(p, sm.tab, b, sm.zbuf[((ly + 1) << p.tw_log2) + lx], xi, yi + 1, bgr, bgg, bgb);
+            const Shaded tr = shade_pixel(p, sm.tab, b, sm.zbuf[((ly + 1) << p.tw_log2) + lx + 1], xi + 1, yi + 1, bgr, bgg, bgb);
+            const Shaded bl = shade_pixel(p, sm.tab, b, sm.zbuf[(ly << p.tw_log2) + lx], xi, yi, bgr, bgg, bgb);
+            const Shaded br = shade_pixel(p, sm.tab, b, sm.zbuf[(ly << p.tw_log2) + lx + 1], xi + 1, yi, bgr, bgg, bgb);
             const size_t otop = (size_t)b * plane + (size_t)(S - 2 - yi) * S + xi;  // row of raster yi+1
             const size_t obot = otop + S;
             *reinterpret_cast<int2*>(p.fim + otop) = make_int2(tl.fim, tr.fim);
@@ -359,7 +404,7 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
     }
     if ((flags & NR_ANTI_ALIASING) && (S & 1)) return NR_ERR_INVALID_ARG;
     if (S > 32767 || B > 65535) return NR_ERR_UNSUPPORTED;
-    if ((size_t)F > (size_t)0x7FFFFFFF - 64) return NR_ERR_UNSUPPORTED;
+    if (F > (1 << 22)) return NR_ERR_UNSUPPORTED;  // z-keys hold a 22-bit face index next to the 10-bit table slot
     const size_t need = nr_b200_forward_workspace_bytes(B, F, S, ts, flags);
     if (!a->workspace || a->workspace_bytes < need || ((uintptr_t)a->workspace & 15)) return NR_ERR_WORKSPACE;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
