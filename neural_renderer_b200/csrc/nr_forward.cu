@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "nr_b200.h"
 #include "nr_math.cuh"
@@ -30,12 +31,11 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kTilePix = 4096;
+// k_raster_tile<kAA, kTL2, kThreads>: tile side 2^kTL2 pixels (32 or 64), kThreads per CTA
 constexpr int kRing = 32;      // per-warp ring of survivors being swept: x0 y0 x1 y1 | x2 y2 fnrec box
 constexpr int kRingWords = 8;
-constexpr int kTab = 512;      // per-tile table of survivor records {inv[9], z[3]} that fragments and the shade pass share
+constexpr int kFwdTileLog2Default = 6, kFwdThreadsDefault = 256;
+constexpr int kTabMax = 512;   // per-tile table of survivor records {inv[9], z[3]} that fragments and the shade pass share
 constexpr int kTabWords = 12;
 constexpr uint32_t kNoRec = 1023;  // z-keys carry (face index << 10 | table slot); 1023 = "not in the table"
 
@@ -61,11 +61,15 @@ struct FwdParams {
 };
 
 // ---------------------------------------------------------------------------------------------- k_raster_tile
+template <int kTL2, int kThreads>
 struct __align__(16) TileShared {
-    unsigned long long zbuf[kTilePix];        // 32 KB  (ordered zp bits << 32 | face index << 10 | table slot), ~0 = empty
-    float tab[kTab][kTabWords];               // 24 KB  survivor records {inv[9], z0, z1, z2} of this tile
-    float ring[kWarps][kRing][kRingWords];    //  8 KB  per-warp sweep records
-    uint32_t fq[kWarps][64];                  //  2 KB  per-warp fragment ring: ring slot << 12 | pixel-in-tile
+    static constexpr int kTilePix = 1 << (2 * kTL2);
+    static constexpr int kTab = kTL2 >= 6 ? kTabMax : kTabMax / 2;
+    static constexpr int kWarps = kThreads / 32;
+    unsigned long long zbuf[kTilePix];        // (ordered zp bits << 32 | face index << 10 | table slot), ~0 = empty
+    float tab[kTab][kTabWords];               // survivor records {inv[9], z0, z1, z2} of this tile
+    float ring[kWarps][kRing][kRingWords];    // per-warp sweep records
+    uint32_t fq[kWarps][64];                  // per-warp fragment ring: ring slot << 12 | pixel-in-tile
     float xp[64];
     float yp[64];
     int next_group;
@@ -135,10 +139,12 @@ __device__ __forceinline__ Shaded shade_pixel(const FwdParams& p, const float (*
     return o;
 }
 
-template <bool kAA>
+template <bool kAA, int kTL2, int kThreads>
 __global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
+    using Shared = TileShared<kTL2, kThreads>;
+    Shared& sm = *reinterpret_cast<Shared*>(smem_raw);
+    constexpr int kTab = Shared::kTab;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
@@ -424,8 +430,14 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
     p.fim = a->face_index_map; p.wmap = a->weight_map; p.dmap = a->depth_map; p.rgb = a->rgb_map; p.alpha = a->alpha_map;
     p.out_rgb = a->out_rgb; p.out_alpha = a->out_alpha; p.out_depth = a->out_depth;
     p.B = B; p.F = F; p.S = S; p.ts = ts; p.nchunks = nchunks;
-    int tl = 6;  // 64x64 tiles; shrink for small rasters so that a tile is not mostly padding
+    int tl = kFwdTileLog2Default, threads = kFwdThreadsDefault;  // tuning knobs: NR_B200_FWD_TILE (5|6), NR_B200_FWD_THREADS (128|256)
+    if (const char* env = getenv("NR_B200_FWD_TILE")) tl = atoi(env) <= 5 ? 5 : 6;
+    if (const char* env = getenv("NR_B200_FWD_THREADS")) threads = atoi(env) == 128 ? 128 : 256;
+    // shrink the tile for small rasters so that it is not mostly padding (the kernels are compiled for 32 / 64 pixel
+    // tiles; smaller rasters run the 32-pixel variant with the tile clipped to the image)
     while (tl > 3 && (1 << (tl - 1)) >= S) tl--;
+    const int tile_log2 = tl;
+    tl = tile_log2 >= 6 ? 6 : 5;
     p.tw_log2 = tl; p.th_log2 = tl;
     p.tiles_x = (S + (1 << tl) - 1) >> tl;
     const int tiles_y = p.tiles_x;
@@ -438,19 +450,25 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
     p.tex_val = (float)tmax;
     p.bg[0] = a->background[0]; p.bg[1] = a->background[1]; p.bg[2] = a->background[2];
 
-    const size_t smem = sizeof(TileShared);
-    cudaError_t e;
-    if (flags & NR_ANTI_ALIASING) {
-        e = cudaFuncSetAttribute(k_raster_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return NR_ERR_CUDA;
-        nr_internal::LaunchScope ls("k_raster_tile", stream);
-        k_raster_tile<true><<<dim3(p.tiles_x * tiles_y, B), kThreads, smem, stream>>>(p);
+    cudaError_t e = cudaSuccess;
+    const dim3 grid(p.tiles_x * tiles_y, B);
+    const bool aa = (flags & NR_ANTI_ALIASING) != 0;
+#define NR_LAUNCH_TILE(AA, TL2, T)                                                                                         \
+    do {                                                                                                                   \
+        const size_t smem = sizeof(TileShared<TL2, T>);                                                                    \
+        e = cudaFuncSetAttribute(k_raster_tile<AA, TL2, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+        if (e != cudaSuccess) return NR_ERR_CUDA;                                                                          \
+        nr_internal::LaunchScope ls("k_raster_tile", stream);                                                              \
+        k_raster_tile<AA, TL2, T><<<grid, T, smem, stream>>>(p);                                                           \
+    } while (0)
+    if (tl >= 6) {
+        if (threads == 128) { if (aa) NR_LAUNCH_TILE(true, 6, 128); else NR_LAUNCH_TILE(false, 6, 128); }
+        else                { if (aa) NR_LAUNCH_TILE(true, 6, 256); else NR_LAUNCH_TILE(false, 6, 256); }
     } else {
-        e = cudaFuncSetAttribute(k_raster_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return NR_ERR_CUDA;
-        nr_internal::LaunchScope ls("k_raster_tile", stream);
-        k_raster_tile<false><<<dim3(p.tiles_x * tiles_y, B), kThreads, smem, stream>>>(p);
+        if (threads == 128) { if (aa) NR_LAUNCH_TILE(true, 5, 128); else NR_LAUNCH_TILE(false, 5, 128); }
+        else                { if (aa) NR_LAUNCH_TILE(true, 5, 256); else NR_LAUNCH_TILE(false, 5, 256); }
     }
+#undef NR_LAUNCH_TILE
     e = cudaGetLastError();
     return e == cudaSuccess ? NR_OK : NR_ERR_CUDA;
 }
