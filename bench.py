@@ -380,18 +380,25 @@ def main():
         fwd_ms = kern.get("k_raster_tile", 0.0)
         dom = max(kern, key=lambda k: kern[k]) if kern else None
 
-        def roof(bytes_, ms_):
+        traffic = {}
+        try:  # DRAM bytes per launch from the committed ncu --set full capture of this shape (profiles/)
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f)["bytes_per_launch"]
+        except Exception:
+            pass
+
+        def roof(bytes_, ms_, kernel=None):
             ach = bytes_ / (ms_ * 1e-3) / 1e9 if ms_ > 0 else 0.0
             return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(ach / peak, 4), "traffic": traffic.get(kernel), "peak_source": peak_src,
                     "algorithmic_bytes": bytes_, "kernel_ms": round(ms_, 5)}
 
         if dom:
             dom_bytes = fwd_bytes if dom == "k_raster_tile" else bwd_bytes
-            out["roofline"] = dict(roof(dom_bytes, kern[dom]), kernel=dom,
+            out["roofline"] = dict(roof(dom_bytes, kern[dom], dom), kernel=dom,
                                    note="algorithmic bytes of the pass the kernel belongs to (SURVEY.md 8(d)) / "
                                         "kernel duration; an ALU/atomic-bound kernel reads far below the HBM roof")
-        out["roofline_fwd"] = dict(roof(fwd_bytes, fwd_ms + kern.get("k_face_bbox", 0.0) / 2), kernel="k_raster_tile",
+        out["roofline_fwd"] = dict(roof(fwd_bytes, fwd_ms + kern.get("k_face_bbox", 0.0) / 2, "k_raster_tile"), kernel="k_raster_tile",
                                    note="forward rasterize = k_face_bbox + k_raster_tile, 391.5 MB algorithmic")
 
         # reference's own kernels on this GPU (the reported baseline of BASELINE.md section 2); N = 1 only
