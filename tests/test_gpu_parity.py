@@ -140,6 +140,59 @@ def test_forward_backward_vs_cpu_oracle(case):
     assert rel_err(np_(got["grad_tex"]), gt) <= TOL
 
 
+# (name, image_size, aa, F, ts, flags, near, far, eps, kind, B, z_range)
+MORE = [
+    ("one_face", 16, False, 1, 2, (1, 1, 1), 0.1, 100, 1e-4, "big", 1, (1.0, 3.0)),
+    ("f33_ts3", 48, False, 33, 3, (1, 1, 1), 0.1, 100, 1e-4, "soup", 2, (1.0, 3.0)),
+    ("f257_ts5", 130, False, 257, 5, (1, 0, 1), 0.1, 100, 1e-3, "soup", 1, (1.0, 3.0)),
+    ("ts8_aa", 40, True, 40, 8, (1, 1, 0), 0.1, 100, 1e-4, "soup", 2, (1.0, 3.0)),
+    ("behind_camera", 64, False, 120, 2, (1, 1, 1), 0.1, 100, 1e-4, "soup", 2, (-1.0, 3.0)),
+    ("depth_aa", 32, True, 60, 2, (0, 0, 1), 0.5, 2.5, 1e-4, "soup", 2, (1.0, 3.0)),
+    ("alpha_aa_big", 96, True, 12, 2, (0, 1, 0), 0.1, 100, 1e-4, "big", 2, (1.0, 3.0)),
+]
+
+
+@pytest.mark.parametrize("case", MORE, ids=[c[0] for c in MORE])
+def test_more_shapes_vs_cpu_oracle(case):
+    """Odd sizes the tiling has to clip (rasters smaller than / not a multiple of the 64-pixel tile, face counts that
+    are not a multiple of the 32-face groups), every texture size, faces behind the camera, anti-aliased single
+    outputs -- all against the CPU oracle."""
+    import nr_oracle as o
+    from neural_renderer_b200 import synthetic
+    name, image_size, aa, F, ts, flags, near, far, eps, kind, B, zr = case
+    seed = zlib.crc32(name.encode()) % 1000
+    size = (0.6, 1.6) if kind == "big" else (0.05, 0.5)
+    faces = synthetic.triangle_soup(B, F, seed=seed, size=size, z_range=zr)
+    tex = synthetic.random_textures(B, F, ts, seed=seed + 7)
+    bg = (0.3, 0.2, 0.1)
+    ref = o.rasterize_rgbad(faces, tex if flags[0] else None, image_size, aa, near, far, eps, bg, *flags)
+    got0 = _run_product(faces, tex, image_size, aa, near, far, eps, bg, flags)
+    grads = _grads(got0, seed=11)
+    got = _run_product(faces, tex, image_size, aa, near, far, eps, bg, flags, grads)
+    assert np.array_equal(np_(got["fim"].flip(1)), ref.fn.face_index_map)
+    for k in ("rgb", "alpha", "depth"):
+        if ref[k] is not None:
+            assert rel_err(np_(got[k]), ref[k]) <= TOL, k
+    gf, gt = ref.backward(*[np_(grads[k]) if k in grads else None for k in ("rgb", "alpha", "depth")])
+    assert rel_err(np_(got["grad_faces"]), gf) <= TOL
+    if flags[0]:
+        assert rel_err(np_(got["grad_tex"]), gt) <= TOL
+
+
+def test_partial_upstream_gradients():
+    """rasterize_rgbad with all three outputs but a loss on alpha only: missing upstream gradients are zeros
+    (rasterize.py:858-878)."""
+    import nr_oracle as o
+    faces, tex = _inputs("soup", 2, 64, 2, seed=21)
+    ref = o.rasterize_rgbad(faces, tex, 32, False, 0.1, 100, 1e-4, (0, 0, 0), True, True, True)
+    got0 = _run_product(faces, tex, 32, False, 0.1, 100, 1e-4, (0, 0, 0), (1, 1, 1))
+    g = _grads(got0, seed=3)
+    got = _run_product(faces, tex, 32, False, 0.1, 100, 1e-4, (0, 0, 0), (1, 1, 1), {"alpha": g["alpha"]})
+    gf, gt = ref.backward(None, np_(g["alpha"]), None)
+    assert rel_err(np_(got["grad_faces"]), gf) <= TOL
+    assert got["grad_tex"] is None or float(got["grad_tex"].abs().max()) == 0.0
+
+
 def test_reference_exact_switch_changes_only_texture_depths():
     """rasterize.py:389 quirk: with per-item geometry the sampler reads batch item 0's vertex depths."""
     import nr_oracle as o
