@@ -125,6 +125,16 @@ NR_B200_API size_t nr_b200_backward_workspace_bytes(int32_t batch_size, int32_t 
 NR_B200_API int nr_b200_forward(const nr_b200_forward_args *args, void *cuda_stream);
 NR_B200_API int nr_b200_backward(const nr_b200_backward_args *args, void *cuda_stream);
 
+/* vertices_to_faces (reference vertices_to_faces.py:4-21), the step either side of the rasterizer:
+ *   forward   out_faces[b,f,k,:] = vertices[b, faces[b,f,k], :]           ([B,Nv,3] x [B,Nf,3] int32 -> [B,Nf,3,3])
+ *   backward  grad_vertices[b, faces[b,f,k], :] += grad_faces[b,f,k,:]   (zero-filled first unless NR_GRAD_ACCUMULATE)
+ * Out-of-range indices gather zeros / are skipped. */
+NR_B200_API int nr_b200_vertices_to_faces(const float *vertices, const int32_t *faces, int32_t batch_size,
+                                          int32_t num_vertices, int32_t num_faces, float *out_faces, void *cuda_stream);
+NR_B200_API int nr_b200_vertices_to_faces_backward(const float *grad_faces, const int32_t *faces, int32_t batch_size,
+                                                   int32_t num_vertices, int32_t num_faces, float *grad_vertices,
+                                                   uint32_t flags, void *cuda_stream);
+
 /* Number of kernels the last forward/backward call on this thread launched (for launch accounting). */
 NR_B200_API int nr_b200_last_launch_count(void);
 

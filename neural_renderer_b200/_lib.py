@@ -30,6 +30,8 @@ EXPORTED_SYMBOLS = (
     "nr_b200_backward_workspace_bytes",
     "nr_b200_forward",
     "nr_b200_backward",
+    "nr_b200_vertices_to_faces",
+    "nr_b200_vertices_to_faces_backward",
     "nr_b200_last_launch_count",
     "nr_b200_set_profiling",
     "nr_b200_read_profile",
@@ -94,6 +96,12 @@ def load():
     lib.nr_b200_forward.argtypes = [ctypes.POINTER(ForwardArgs), ctypes.c_void_p]
     lib.nr_b200_backward.restype = ctypes.c_int
     lib.nr_b200_backward.argtypes = [ctypes.POINTER(BackwardArgs), ctypes.c_void_p]
+    lib.nr_b200_vertices_to_faces.restype = ctypes.c_int
+    lib.nr_b200_vertices_to_faces.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    lib.nr_b200_vertices_to_faces_backward.restype = ctypes.c_int
+    lib.nr_b200_vertices_to_faces_backward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                                       ctypes.c_int32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
     lib.nr_b200_last_launch_count.restype = ctypes.c_int
     lib.nr_b200_set_profiling.restype = None
     lib.nr_b200_set_profiling.argtypes = [ctypes.c_int]

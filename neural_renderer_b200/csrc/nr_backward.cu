@@ -191,48 +191,50 @@ __global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ 
     const bool aa = (p.flags & NR_ANTI_ALIASING) != 0;
     const size_t plane = (size_t)S * S;
 
-    // ---- 1. stage the strip (image orientation in global memory: raster row y is stored at row S-1-y)
-    for (int i = tid; i < nlines * Sp; i += kThreads) {
-        int line, d1;
-        if (axis == 0) { line = i % nlines; d1 = i / nlines; }   // columns: d0 = x, d1 = y
-        else           { line = i / Sp;     d1 = i % Sp; }
-        float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        float A = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f, ga = 0.f;
-        if (d1 < S) {  // (the padding pixel of an odd raster size stays zero)
-            const int x = (axis == 0) ? l0 + line : d1, y = (axis == 0) ? d1 : l0 + line;
-            const int row = S - 1 - y;
-            const size_t o = (size_t)row * S + x;
-            const int fi = __ldg(p.fim + (size_t)b * plane + o);
-            c.w = __int_as_float(fi);
-            const float alpha = fi >= 0 ? 1.0f : 0.0f;
-            if (kMode == 2) {
-                g0 = load_grad(p.g_alpha, aa, S, (size_t)b, row, x);
-                c.x = alpha;
-                A = alpha * g0;
-            } else {
-                const float* rm = p.rgb + (size_t)b * 3 * plane + o;
-                c.x = __ldg(rm); c.y = __ldg(rm + plane); c.z = __ldg(rm + 2 * plane);
-                g0 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 0, row, x);
-                g1 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 1, row, x);
-                g2 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 2, row, x);
-                float acc = 0.0f;
-                if (kMode == 3) {
-                    ga = load_grad(p.g_alpha, aa, S, (size_t)b, row, x);
-                    acc = alpha * ga;
-                }
-                A = __fmaf_rn(c.z, g2, __fmaf_rn(c.y, g1, __fmaf_rn(c.x, g0, acc)));
+    // ---- 1. stage the strip (image orientation in global memory: raster row y is stored at row S-1-y).
+    //         One thread per pixel PAIR of a line: 16-byte shared-memory stores, half the index arithmetic.
+    struct Px { float A, g0, g1, g2, ga; float4 c; };
+    auto load_px = [&](int line, int d1) {
+        Px q;
+        q.c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        q.A = q.g0 = q.g1 = q.g2 = q.ga = 0.f;
+        if (d1 >= S) return q;  // the padding pixel of an odd raster size stays zero
+        const int x = (axis == 0) ? l0 + line : d1, y = (axis == 0) ? d1 : l0 + line;
+        const int row = S - 1 - y;
+        const size_t o = (size_t)row * S + x;
+        const int fi = __ldg(p.fim + (size_t)b * plane + o);
+        q.c.w = __int_as_float(fi);
+        const float alpha = fi >= 0 ? 1.0f : 0.0f;
+        if (kMode == 2) {
+            q.g0 = load_grad(p.g_alpha, aa, S, (size_t)b, row, x);
+            q.c.x = alpha;
+            q.A = alpha * q.g0;
+        } else {
+            const float* rm = p.rgb + (size_t)b * 3 * plane + o;
+            q.c.x = __ldg(rm); q.c.y = __ldg(rm + plane); q.c.z = __ldg(rm + 2 * plane);
+            q.g0 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 0, row, x);
+            q.g1 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 1, row, x);
+            q.g2 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 2, row, x);
+            float acc = 0.0f;
+            if (kMode == 3) {
+                q.ga = load_grad(p.g_alpha, aa, S, (size_t)b, row, x);
+                acc = alpha * q.ga;
             }
+            q.A = __fmaf_rn(q.c.z, q.g2, __fmaf_rn(q.c.y, q.g1, __fmaf_rn(q.c.x, q.g0, acc)));
         }
-        const size_t pi = (size_t)line * npair + (d1 >> 1);
-        const int h = d1 & 1;
-        reinterpret_cast<float*>(P + pi)[h] = A;
-        reinterpret_cast<float*>(P + pi)[2 + h] = g0;
-        if (kMode != 2) {
-            reinterpret_cast<float*>(Q + pi)[h] = g1;
-            reinterpret_cast<float*>(Q + pi)[2 + h] = g2;
-        }
-        if (kMode == 3) reinterpret_cast<float*>(R + pi)[h] = ga;
-        ci[(size_t)line * Sp + d1] = c;
+        return q;
+    };
+    for (int i = tid; i < nlines * npair; i += kThreads) {
+        int line, pp;
+        if (axis == 0) { line = i % nlines; pp = i / nlines; }   // columns: d0 = x, d1 = y
+        else           { line = i / npair;  pp = i % npair; }
+        const Px e = load_px(line, 2 * pp), o = load_px(line, 2 * pp + 1);
+        const size_t pi = (size_t)line * npair + pp;
+        P[pi] = make_float4(e.A, o.A, e.g0, o.g0);
+        if (kMode != 2) Q[pi] = make_float4(e.g1, o.g1, e.g2, o.g2);
+        if (kMode == 3) R[pi] = make_float2(e.ga, o.ga);
+        ci[(size_t)line * Sp + 2 * pp] = e.c;
+        ci[(size_t)line * Sp + 2 * pp + 1] = o.c;
     }
     if (tid < 32) s_hist[tid] = 0;
     if (tid == 0) { s_nface = 0; s_ntask = 0; s_next = 0; }

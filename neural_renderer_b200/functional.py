@@ -139,6 +139,41 @@ def lighting(faces, textures, intensity_ambient=0.5, intensity_directional=0.5, 
     return textures * light[:, :, None, None, None, :]
 
 
+class _VerticesToFaces(torch.autograd.Function):
+    """CUDA gather (forward) / scatter-add (backward) behind the C ABI (nr_b200_vertices_to_faces*)."""
+
+    @staticmethod
+    def forward(ctx, vertices, faces_i32):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        v = vertices.detach().contiguous()
+        bs, nv = v.shape[:2]
+        nf = faces_i32.shape[1]
+        out = torch.empty((bs, nf, 3, 3), dtype=torch.float32, device=v.device)
+        with torch.cuda.device(v.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(v.device).cuda_stream)
+            _lib.check(lib.nr_b200_vertices_to_faces(v.data_ptr(), faces_i32.data_ptr(), bs, nv, nf, out.data_ptr(), stream))
+        ctx.save_for_backward(faces_i32)
+        ctx.nv = nv
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        faces_i32, = ctx.saved_tensors
+        g = grad_out.detach().to(torch.float32).contiguous()
+        bs, nf = g.shape[:2]
+        grad_v = torch.empty((bs, ctx.nv, 3), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
+            _lib.check(lib.nr_b200_vertices_to_faces_backward(g.data_ptr(), faces_i32.data_ptr(), bs, ctx.nv, nf,
+                                                              grad_v.data_ptr(), 0, stream))
+        return grad_v, None
+
+
 def vertices_to_faces(vertices, faces):
     """[B,Nv,3] x [B,Nf,3] int -> [B,Nf,3,3]"""
     assert vertices.dim() == 3
@@ -147,5 +182,7 @@ def vertices_to_faces(vertices, faces):
     assert vertices.shape[2] == 3
     assert faces.shape[2] == 3
     bs, nv = vertices.shape[:2]
+    if vertices.is_cuda and faces.is_cuda and vertices.dtype == torch.float32 and bs <= 65535:
+        return _VerticesToFaces.apply(vertices, faces.to(torch.int32).contiguous())
     idx = faces.long() + (torch.arange(bs, device=faces.device, dtype=torch.long) * nv)[:, None, None]
     return vertices.reshape(bs * nv, 3)[idx]

@@ -366,6 +366,25 @@ def test_headline_vs_reference_kernels(headline):
     assert rel_err(np_(got["grad_tex"]), np_(gt)) <= TOL
 
 
+def test_vertices_to_faces_kernels(teapot):
+    """Fused gather / scatter-add (nr_b200_vertices_to_faces*) against plain torch indexing (vertices_to_faces.py:16-21)."""
+    import neural_renderer as nr
+    dev = torch.device("cuda")
+    v, f = teapot
+    B = 3
+    vert = torch.from_numpy(np.stack([v * (1 + 0.1 * i) for i in range(B)])).to(dev).requires_grad_(True)
+    faces = torch.from_numpy(np.stack([f] * B)).to(dev)
+    out = nr.vertices_to_faces(vert, faces)
+    idx = faces.long() + (torch.arange(B, device=dev) * v.shape[0])[:, None, None]
+    ref_in = vert.detach().clone().requires_grad_(True)
+    ref = ref_in.reshape(-1, 3)[idx]
+    assert torch.equal(out, ref)
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(4)).to(dev)
+    (out * g).sum().backward()
+    (ref * g).sum().backward()
+    assert rel_err(np_(vert.grad), np_(ref_in.grad)) <= 1e-5
+
+
 def test_edge_cases():
     """Empty / degenerate inputs the reference's tests exercise implicitly (all-zero batch slots of to_minibatch),
     single face, faces entirely off screen, rgb + per-batch background."""
