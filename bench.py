@@ -141,8 +141,9 @@ def ours_step(faces, tex, grad):
     faces.grad = None
     tex.grad = None
     img = nr.rasterize(faces, tex, w["image_size"], w["anti_aliasing"], w["near"], w["far"], w["eps"], w["background"])
-    loss = (img * grad).sum()
-    loss.backward()
+    img.backward(grad)  # upstream gradient dL/dI = grad, i.e. L = sum(I * grad)
+    with torch.no_grad():
+        loss = (img * grad).sum()
     return loss
 
 
@@ -151,8 +152,8 @@ def ref_gpu_step(faces, tex, grad):
     w = WORKLOAD
     res = refhost.rasterize_rgbad(faces, tex, w["image_size"], w["anti_aliasing"], w["near"], w["far"], w["eps"],
                                   w["background"], True, False, False)
+    gf, gt = res.backward(grad, None, None)  # same upstream gradient as the other arm
     loss = (res["rgb"] * grad).sum()
-    gf, gt = res.backward(grad, None, None)
     return loss, gf, gt
 
 

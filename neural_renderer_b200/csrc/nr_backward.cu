@@ -115,16 +115,21 @@ __global__ void __launch_bounds__(256) k_strip_bin(const uint2* __restrict__ bbo
     }
 }
 
-// exclusive prefix sum of n counters by one CTA (n = B * 2 * (nstrips + 1): a few thousand to ~10^5)
-__global__ void __launch_bounds__(1024) k_strip_scan(const int* __restrict__ cnt, int* __restrict__ off, int n) {
-    __shared__ int warp_sum[32];
+// Exclusive prefix sum of the nstrips + 1 counters of one (item, axis) segment; every segment owns a fixed region of
+// the list storage (seg_stride entries: at most kWideStrips per face), so segments are scanned independently.
+__global__ void __launch_bounds__(256) k_strip_scan(const int* __restrict__ cnt, int* __restrict__ off, int seg_len,
+                                                    long long seg_stride) {
+    __shared__ int warp_sum[8];
     __shared__ int carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t seg = blockIdx.x;
+    cnt += seg * seg_len;
+    off += seg * seg_len;
     if (tid == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
+    for (int base = 0; base < seg_len; base += 256) {
         const int i = base + tid;
-        const int v = i < n ? cnt[i] : 0;
+        const int v = i < seg_len ? cnt[i] : 0;
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -134,20 +139,20 @@ __global__ void __launch_bounds__(1024) k_strip_scan(const int* __restrict__ cnt
         if (lane == 31) warp_sum[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            const int w = warp_sum[lane];
+            const int w = lane < 8 ? warp_sum[lane] : 0;
             int wi = w;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
+            for (int o = 1; o < 8; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, wi, o);
                 if (lane >= o) wi += t;
             }
-            warp_sum[lane] = wi - w;  // exclusive
+            if (lane < 8) warp_sum[lane] = wi - w;  // exclusive
         }
         __syncthreads();
         const int c = carry;
-        if (i < n) off[i] = c + warp_sum[warp] + incl - v;
+        if (i < seg_len) off[i] = (int)(seg * seg_stride) + c + warp_sum[warp] + incl - v;
         __syncthreads();
-        if (tid == 1023) carry = c + warp_sum[warp] + incl;
+        if (tid == 255) carry = c + warp_sum[warp] + incl;
         __syncthreads();
     }
 }
@@ -168,7 +173,7 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f
 //   ci[i] = {I0, I1, I2, fim}        colours and face index per pixel: task set-up and the short in-scan only
 // kMode: 1 = rgb, 2 = alpha only (g0 = g_alpha, I0 = alpha), 3 = rgb + alpha
 template <int kMode, int kThreads>
-__global__ void __launch_bounds__(kThreads) k_edge_scan(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const __grid_constant__ BwdParams p) {
     constexpr int kFaceQueue = 2 * kThreads, kTaskCap = 8 * kThreads;
     static_assert(kFaceQueue <= 512 && kTaskCap <= 4096, "task word layout");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -674,6 +679,7 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
     if (rgb && (!a->rgb_map || !a->grad_textures || ts < 2)) return NR_ERR_INVALID_ARG;
     if ((flags & NR_ANTI_ALIASING) && (S & 1)) return NR_ERR_INVALID_ARG;
     if (S > 32767 || B > 65535) return NR_ERR_UNSUPPORTED;
+    if ((size_t)B * F * 2 * kWideStrips >= (size_t)0x7FFFFFFF) return NR_ERR_UNSUPPORTED;  // 32-bit list offsets
     const size_t need = nr_b200_backward_workspace_bytes(B, F, S, ts, flags);
     if (!a->workspace || a->workspace_bytes < need || ((uintptr_t)a->workspace & 15)) return NR_ERR_WORKSPACE;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
@@ -733,7 +739,7 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
             }
             {
                 nr_internal::LaunchScope ls("k_strip_scan", stream);
-                k_strip_scan<<<1, 1024, 0, stream>>>(cnt, off, (int)L.ncounters);
+                k_strip_scan<<<B * 2, 256, 0, stream>>>(cnt, off, nstrips + 1, (long long)F * kWideStrips);
             }
             {
                 nr_internal::LaunchScope ls("k_strip_bin", stream);
