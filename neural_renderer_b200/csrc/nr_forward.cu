@@ -72,6 +72,7 @@ struct __align__(16) TileShared {
     uint32_t fq[kWarps][64];                  // per-warp fragment ring: ring slot << 12 | pixel-in-tile
     float xp[64];
     float yp[64];
+    int rowpre[kWarps][32];                   // per-warp: first row number of each survivor of the current group
     int next_group;
     int tab_count;
 };
@@ -227,11 +228,13 @@ __global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant_
             const uint32_t m = __ballot_sync(0xffffffffu, pass);
             if (m == 0u) continue;
             const int nsurv = __popc(m);
-            // sweep records of faces that still have queued fragments must not be overwritten (fragments are queued in
-            // record order, so the oldest one sits at the head of the queue)
+            // sweep records of faces that still have queued fragments must not be overwritten
             if (fq_n > 0) {
-                const int oldest = (int)(fq[fq_head] >> 12);
-                if ((((ring_head - oldest - 1) & (kRing - 1)) + 1) + nsurv > kRing) drain(fq_n);
+                int d = 0;  // fragments of several faces interleave in the queue: take the oldest record over all of them
+                if (lane < fq_n) d = ((ring_head - (int)(fq[(fq_head + lane) & 63] >> 12) - 1) & (kRing - 1)) + 1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, o));
+                if (d + nsurv > kRing) drain(fq_n);
             }
             int tbase = 0;
             if (lane == 0) tbase = atomicAdd(&sm.tab_count, nsurv);
@@ -261,38 +264,86 @@ __global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant_
                 r4[1] = make_float4(c[6], c[7], __uint_as_float(((uint32_t)f << 10) | rec), __uint_as_float(box));
             }
             __syncwarp();
-            for (int j = 0; j < nsurv; j++) {
-                const int slot = (ring_head + j) & (kRing - 1);
-                const float4* r4 = reinterpret_cast<const float4*>(ring[slot]);
-                const float4 q0 = r4[0], q1 = r4[1];
-                const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y;
-                const uint32_t box = __float_as_uint(q1.w);
-                const int lx0 = box & 0xFF, lx1 = (box >> 8) & 0xFF, ly0 = (box >> 16) & 0xFF, ly1 = box >> 24;
-                const float dx10 = __fsub_rn(x1, x0), dy10 = __fsub_rn(y1, y0), dx21 = __fsub_rn(x2, x1),
-                            dy21 = __fsub_rn(y2, y1), dx02 = __fsub_rn(x0, x2), dy02 = __fsub_rn(y0, y2);
-                const uint32_t slot_bits = (uint32_t)slot << 12;
-                for (int oy = ly0; oy <= ly1; oy += 4) {
-                    const int ly = oy + (lane >> 3);
-                    // the row terms of the three edge functions do not change along a row of 8x4 blocks
-                    const float yp = sm.yp[min(ly, 63)];
-                    const float r0 = __fmul_rn(__fsub_rn(yp, y0), dx10), r1 = __fmul_rn(__fsub_rn(yp, y1), dx21),
-                                r2 = __fmul_rn(__fsub_rn(yp, y2), dx02);
-                    const bool row_ok = ly <= ly1;
-                    const uint32_t pix_row = (uint32_t)(ly << p.tw_log2);
-                    for (int lx = lx0 + (lane & 7); __any_sync(0xffffffffu, lx <= lx1); lx += 8) {
-                        const float xp = sm.xp[lx & 63];
-                        const int o0 = r0 < __fmul_rn(__fsub_rn(xp, x0), dy10);
-                        const int o1 = r1 < __fmul_rn(__fsub_rn(xp, x1), dy21);
-                        const int o2 = r2 < __fmul_rn(__fsub_rn(xp, x2), dy02);
-                        const bool in = row_ok && (lx <= lx1) && ((o0 | o1 | o2) == 0);
+            // ---- row-span rasterization.  For a fixed pixel row each edge test  r_k < (xp - x_k) * dy_k  is monotone in
+            //      x (xp increases with x; rounded subtraction and multiplication are monotone), so the pixels that
+            //      pass all three tests form one interval [lo, hi].  Its ends are found by binary search with the
+            //      reference's own expressions -- the coverage is identical, but a row costs O(log width) tests.
+            //      Lanes = rows of the group's survivors (flattened over faces), 32 rows per pass.
+            {
+                const int h = pass ? (by1 - by0 + 1) : 0;
+                int incl = h;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int nrows = __shfl_sync(0xffffffffu, incl, 31);
+                int* rowpre = sm.rowpre[warp];
+                rowpre[lane] = incl - h;
+                __syncwarp();
+                for (int base = 0; base < nrows; base += 32) {
+                    const int r = base + lane;
+                    int lo = 1, hi = 0, slot = 0;
+                    uint32_t pix_row = 0;
+                    if (r < nrows) {
+                        // owner = last lane whose first row is <= r  (upper_bound - 1 over the non-decreasing prefix)
+                        int a = 0, bnd = 32;
+#pragma unroll
+                        for (int it = 0; it < 5; it++) {
+                            const int mid = (a + bnd) >> 1;
+                            if (rowpre[mid] <= r) a = mid; else bnd = mid;
+                        }
+                        const int owner = a;
+                        slot = (ring_head + __popc(m & ((1u << owner) - 1u))) & (kRing - 1);
+                        const float4* r4 = reinterpret_cast<const float4*>(ring[slot]);
+                        const float4 q0 = r4[0], q1 = r4[1];
+                        const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y;
+                        const uint32_t box = __float_as_uint(q1.w);
+                        const int lx0 = box & 0xFF, lx1 = (box >> 8) & 0xFF;
+                        const int ly = (int)((box >> 16) & 0xFF) + (r - rowpre[owner]);
+                        pix_row = (uint32_t)(ly << p.tw_log2);
+                        const float yp = sm.yp[ly];
+                        const float xk[3] = {x0, x1, x2};
+                        const float dyk[3] = {__fsub_rn(y1, y0), __fsub_rn(y2, y1), __fsub_rn(y0, y2)};
+                        const float rk[3] = {__fmul_rn(__fsub_rn(yp, y0), __fsub_rn(x1, x0)),
+                                             __fmul_rn(__fsub_rn(yp, y1), __fsub_rn(x2, x1)),
+                                             __fmul_rn(__fsub_rn(yp, y2), __fsub_rn(x0, x2))};
+                        lo = lx0; hi = lx1;
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const float xe = xk[k], dy = dyk[k], rr = rk[k];
+                            // out(x) = rr < (xp(x) - xe) * dy : non-decreasing in x for dy > 0, non-increasing for dy < 0
+                            if (dy > 0.0f) {          // allowed pixels: x < first x with out(x)
+                                int a2 = lo, b2 = hi + 1;
+                                while (a2 < b2) {
+                                    const int mid = (a2 + b2) >> 1;
+                                    if (rr < __fmul_rn(__fsub_rn(sm.xp[mid], xe), dy)) b2 = mid; else a2 = mid + 1;
+                                }
+                                hi = a2 - 1;
+                            } else if (dy < 0.0f) {   // allowed pixels: x >= first x with !out(x)
+                                int a2 = lo, b2 = hi + 1;
+                                while (a2 < b2) {
+                                    const int mid = (a2 + b2) >> 1;
+                                    if (!(rr < __fmul_rn(__fsub_rn(sm.xp[mid], xe), dy))) b2 = mid; else a2 = mid + 1;
+                                }
+                                lo = a2;
+                            } else {                  // dy == 0: the test does not depend on x
+                                if (rr < __fmul_rn(__fsub_rn(sm.xp[lo], xe), dy)) hi = lo - 1;
+                            }
+                        }
+                    }
+                    // emit the spans, one pixel per lane and round, compacted into the fragment queue
+                    const uint32_t slot_bits = (uint32_t)slot << 12;
+                    for (int x = lo; __any_sync(0xffffffffu, x <= hi); x++) {
+                        const bool in = x <= hi;
                         const uint32_t mi = __ballot_sync(0xffffffffu, in);
-                        if (mi == 0u) continue;
-                        if (in) fq[(fq_head + fq_n + __popc(mi & lt_mask)) & 63] = slot_bits | (pix_row + (uint32_t)lx);
+                        if (in) fq[(fq_head + fq_n + __popc(mi & lt_mask)) & 63] = slot_bits | (pix_row + (uint32_t)x);
                         fq_n += __popc(mi);
                         __syncwarp();
                         if (fq_n >= 32) drain(32);
                     }
                 }
+                __syncwarp();
             }
             ring_head = (ring_head + nsurv) & (kRing - 1);
         }
