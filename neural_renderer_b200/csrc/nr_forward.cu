@@ -32,7 +32,7 @@
 namespace {
 
 // k_raster_tile<kAA, kTL2, kThreads>: tile side 2^kTL2 pixels (32 or 64), kThreads per CTA
-constexpr int kRing = 32;      // per-warp ring of survivors being swept: x0 y0 x1 y1 | x2 y2 fnrec box
+constexpr int kRing = 32;      // per-warp scratch of the current group's survivors: x0 y0 x1 y1 | x2 y2 fnrec box
 constexpr int kRingWords = 8;
 constexpr int kFwdTileLog2Default = 6, kFwdThreadsDefault = 256;
 constexpr int kTabMax = 512;   // per-tile table of survivor records {inv[9], z[3]} that fragments and the shade pass share
@@ -69,10 +69,10 @@ struct __align__(16) TileShared {
     unsigned long long zbuf[kTilePix];        // (ordered zp bits << 32 | face index << 10 | table slot), ~0 = empty
     float tab[kTab][kTabWords];               // survivor records {inv[9], z0, z1, z2} of this tile
     float ring[kWarps][kRing][kRingWords];    // per-warp sweep records
-    uint32_t fq[kWarps][64];                  // per-warp fragment ring: ring slot << 12 | pixel-in-tile
     float xp[64];
     float yp[64];
     int rowpre[kWarps][32];                   // per-warp: first row number of each survivor of the current group
+    int spanpre[kWarps][32];                  // per-warp: first fragment number of each row span of the current pass
     int next_group;
     int tab_count;
 };
@@ -171,41 +171,11 @@ __global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant_
         const uint2* bbox = p.bbox + (size_t)b * p.F;
         const uint2* cbox = p.chunk_bbox + (size_t)b * p.nchunks;
         float(*ring)[kRingWords] = sm.ring[warp];
-        uint32_t* fq = sm.fq[warp];
+        int* rowpre = sm.rowpre[warp];
+        int* spanpre = sm.spanpre[warp];
         unsigned long long* zbuf = sm.zbuf;
         const float fS = (float)p.S;
         const uint32_t lt_mask = (1u << lane) - 1u;
-        int ring_head = 0, fq_head = 0, fq_n = 0;
-
-        auto drain = [&](int cnt) {
-            if (lane < cnt) {
-                const uint32_t e = fq[(fq_head + lane) & 63];
-                const int slot = (int)(e >> 12), pix = (int)(e & 4095u);
-                const uint32_t fnrec = __float_as_uint(ring[slot][6]);
-                const uint32_t rec = fnrec & 1023u;
-                float inv[9], z[3];
-                if (rec != kNoRec) {
-                    const float4* t4 = reinterpret_cast<const float4*>(sm.tab[rec]);
-                    const float4 a = t4[0], bb = t4[1], cc = t4[2];
-                    inv[0] = a.x; inv[1] = a.y; inv[2] = a.z; inv[3] = a.w; inv[4] = bb.x; inv[5] = bb.y; inv[6] = bb.z; inv[7] = bb.w;
-                    inv[8] = cc.x; z[0] = cc.y; z[1] = cc.z; z[2] = cc.w;
-                } else {
-                    face_record(p, b, (int)(fnrec >> 10), inv, z);  // tile with more than kTab survivors
-                }
-                const int lx = pix & (tw - 1), ly = pix >> p.tw_log2;
-                float w[3];
-                const float zp = nr::weights_and_depth(inv, (float)(tx0 + lx), (float)(ty0 + ly), z[0], z[1], z[2], w);
-                // rasterize.py:331 + :334 against the initial depth_min = far; NaN fails both (never wins)
-                if (zp > p.near_lo && zp < p.far_cmp) {
-                    const unsigned long long key = ((unsigned long long)nr::float_to_ordered(zp) << 32) | fnrec;
-                    unsigned long long* addr = zbuf + pix;
-                    if (key < *reinterpret_cast<volatile unsigned long long*>(addr)) atomicMin(addr, key);
-                }
-            }
-            fq_head = (fq_head + cnt) & 63;
-            fq_n -= cnt;
-            __syncwarp();  // queue entries / ring records just read may be overwritten by the next push
-        };
 
         while (true) {
             int g = 0;
@@ -228,20 +198,13 @@ __global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant_
             const uint32_t m = __ballot_sync(0xffffffffu, pass);
             if (m == 0u) continue;
             const int nsurv = __popc(m);
-            // sweep records of faces that still have queued fragments must not be overwritten
-            if (fq_n > 0) {
-                int d = 0;  // fragments of several faces interleave in the queue: take the oldest record over all of them
-                if (lane < fq_n) d = ((ring_head - (int)(fq[(fq_head + lane) & 63] >> 12) - 1) & (kRing - 1)) + 1;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, o));
-                if (d + nsurv > kRing) drain(fq_n);
-            }
             int tbase = 0;
             if (lane == 0) tbase = atomicAdd(&sm.tab_count, nsurv);
             tbase = __shfl_sync(0xffffffffu, tbase, 0);
             if (pass) {
+                // survivor set-up, one face per lane: sweep record (vertices, clipped box) into the warp's scratch ring,
+                // exact K1 inverse into the tile's record table
                 const int rank = __popc(m & lt_mask);
-                const int slot = (ring_head + rank) & (kRing - 1);
                 const int trec = tbase + rank;
                 const uint32_t rec = trec < kTab ? (uint32_t)trec : kNoRec;
                 const float* v = p.faces + ((size_t)b * p.F + f) * 9;
@@ -257,97 +220,119 @@ __global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant_
                     t4[1] = make_float4(inv[4], inv[5], inv[6], inv[7]);
                     t4[2] = make_float4(inv[8], c[2], c[5], c[8]);
                 }
-                float4* r4 = reinterpret_cast<float4*>(ring[slot]);
+                float4* r4 = reinterpret_cast<float4*>(ring[rank]);
                 r4[0] = make_float4(c[0], c[1], c[3], c[4]);
                 const uint32_t box = (uint32_t)(bx0 - tx0) | ((uint32_t)(bx1 - tx0) << 8) | ((uint32_t)(by0 - ty0) << 16) |
                                      ((uint32_t)(by1 - ty0) << 24);
                 r4[1] = make_float4(c[6], c[7], __uint_as_float(((uint32_t)f << 10) | rec), __uint_as_float(box));
             }
-            __syncwarp();
             // ---- row-span rasterization.  For a fixed pixel row each edge test  r_k < (xp - x_k) * dy_k  is monotone in
             //      x (xp increases with x; rounded subtraction and multiplication are monotone), so the pixels that
             //      pass all three tests form one interval [lo, hi].  Its ends are found by binary search with the
             //      reference's own expressions -- the coverage is identical, but a row costs O(log width) tests.
-            //      Lanes = rows of the group's survivors (flattened over faces), 32 rows per pass.
-            {
-                const int h = pass ? (by1 - by0 + 1) : 0;
-                int incl = h;
+            //      Lanes = rows of the group's survivors (flattened over faces), 32 rows per pass; the pixels of the
+            //      32 spans are then flattened again and evaluated 32 fragments at a time.
+            const int h = pass ? (by1 - by0 + 1) : 0;
+            int incl = h;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int nrows = __shfl_sync(0xffffffffu, incl, 31);
+            rowpre[lane] = incl - h;
+            __syncwarp();
+            for (int base = 0; base < nrows; base += 32) {
+                const int r = base + lane;
+                int lo = 1, hi = 0;
+                uint32_t fnrec = 0, pix_row = 0;
+                if (r < nrows) {
+                    // owner = last lane whose first row is <= r  (upper_bound - 1 over the non-decreasing prefix)
+                    int a = 0, bnd = 32;
+#pragma unroll
+                    for (int it = 0; it < 5; it++) {
+                        const int mid = (a + bnd) >> 1;
+                        if (rowpre[mid] <= r) a = mid; else bnd = mid;
+                    }
+                    const float4* r4 = reinterpret_cast<const float4*>(ring[__popc(m & ((1u << a) - 1u))]);
+                    const float4 q0 = r4[0], q1 = r4[1];
+                    const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y;
+                    fnrec = __float_as_uint(q1.z);
+                    const uint32_t box = __float_as_uint(q1.w);
+                    const int ly = (int)((box >> 16) & 0xFF) + (r - rowpre[a]);
+                    pix_row = (uint32_t)(ly << p.tw_log2);
+                    const float yp = sm.yp[ly];
+                    const float xk[3] = {x0, x1, x2};
+                    const float dyk[3] = {__fsub_rn(y1, y0), __fsub_rn(y2, y1), __fsub_rn(y0, y2)};
+                    const float rk[3] = {__fmul_rn(__fsub_rn(yp, y0), __fsub_rn(x1, x0)),
+                                         __fmul_rn(__fsub_rn(yp, y1), __fsub_rn(x2, x1)),
+                                         __fmul_rn(__fsub_rn(yp, y2), __fsub_rn(x0, x2))};
+                    lo = box & 0xFF; hi = (box >> 8) & 0xFF;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const float xe = xk[k], dy = dyk[k], rr = rk[k];
+                        // out(x) = rr < (xp(x) - xe) * dy is non-decreasing in x for dy >= 0 (constant for dy == 0) and
+                        // non-increasing for dy < 0: find the first x where out(x) != (dy < 0)
+                        const bool neg = dy < 0.0f;
+                        int a2 = lo, b2 = hi + 1;
+                        while (a2 < b2) {
+                            const int mid = (a2 + b2) >> 1;
+                            const bool out = rr < __fmul_rn(__fsub_rn(sm.xp[mid], xe), dy);
+                            if (out != neg) b2 = mid; else a2 = mid + 1;
+                        }
+                        if (neg) lo = a2; else hi = a2 - 1;
+                    }
+                }
+                // flatten the 32 spans into fragments
+                const int n = max(hi - lo + 1, 0);
+                int sincl = n;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
+                    const int t = __shfl_up_sync(0xffffffffu, sincl, o);
+                    if (lane >= o) sincl += t;
                 }
-                const int nrows = __shfl_sync(0xffffffffu, incl, 31);
-                int* rowpre = sm.rowpre[warp];
-                rowpre[lane] = incl - h;
+                const int nfrag = __shfl_sync(0xffffffffu, sincl, 31);
+                spanpre[lane] = sincl - n;
                 __syncwarp();
-                for (int base = 0; base < nrows; base += 32) {
-                    const int r = base + lane;
-                    int lo = 1, hi = 0, slot = 0;
-                    uint32_t pix_row = 0;
-                    if (r < nrows) {
-                        // owner = last lane whose first row is <= r  (upper_bound - 1 over the non-decreasing prefix)
-                        int a = 0, bnd = 32;
+                for (int fb = 0; fb < nfrag; fb += 32) {
+                    const int i = fb + lane;
+                    // all lanes take part in the shuffles; lanes past the end evaluate nothing
+                    int a = 0, bnd = 32;
 #pragma unroll
-                        for (int it = 0; it < 5; it++) {
-                            const int mid = (a + bnd) >> 1;
-                            if (rowpre[mid] <= r) a = mid; else bnd = mid;
-                        }
-                        const int owner = a;
-                        slot = (ring_head + __popc(m & ((1u << owner) - 1u))) & (kRing - 1);
-                        const float4* r4 = reinterpret_cast<const float4*>(ring[slot]);
-                        const float4 q0 = r4[0], q1 = r4[1];
-                        const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y;
-                        const uint32_t box = __float_as_uint(q1.w);
-                        const int lx0 = box & 0xFF, lx1 = (box >> 8) & 0xFF;
-                        const int ly = (int)((box >> 16) & 0xFF) + (r - rowpre[owner]);
-                        pix_row = (uint32_t)(ly << p.tw_log2);
-                        const float yp = sm.yp[ly];
-                        const float xk[3] = {x0, x1, x2};
-                        const float dyk[3] = {__fsub_rn(y1, y0), __fsub_rn(y2, y1), __fsub_rn(y0, y2)};
-                        const float rk[3] = {__fmul_rn(__fsub_rn(yp, y0), __fsub_rn(x1, x0)),
-                                             __fmul_rn(__fsub_rn(yp, y1), __fsub_rn(x2, x1)),
-                                             __fmul_rn(__fsub_rn(yp, y2), __fsub_rn(x0, x2))};
-                        lo = lx0; hi = lx1;
-#pragma unroll
-                        for (int k = 0; k < 3; k++) {
-                            const float xe = xk[k], dy = dyk[k], rr = rk[k];
-                            // out(x) = rr < (xp(x) - xe) * dy : non-decreasing in x for dy > 0, non-increasing for dy < 0
-                            if (dy > 0.0f) {          // allowed pixels: x < first x with out(x)
-                                int a2 = lo, b2 = hi + 1;
-                                while (a2 < b2) {
-                                    const int mid = (a2 + b2) >> 1;
-                                    if (rr < __fmul_rn(__fsub_rn(sm.xp[mid], xe), dy)) b2 = mid; else a2 = mid + 1;
-                                }
-                                hi = a2 - 1;
-                            } else if (dy < 0.0f) {   // allowed pixels: x >= first x with !out(x)
-                                int a2 = lo, b2 = hi + 1;
-                                while (a2 < b2) {
-                                    const int mid = (a2 + b2) >> 1;
-                                    if (!(rr < __fmul_rn(__fsub_rn(sm.xp[mid], xe), dy))) b2 = mid; else a2 = mid + 1;
-                                }
-                                lo = a2;
-                            } else {                  // dy == 0: the test does not depend on x
-                                if (rr < __fmul_rn(__fsub_rn(sm.xp[lo], xe), dy)) hi = lo - 1;
-                            }
-                        }
+                    for (int it = 0; it < 5; it++) {
+                        const int mid = (a + bnd) >> 1;
+                        if (spanpre[mid] <= i) a = mid; else bnd = mid;
                     }
-                    // emit the spans, one pixel per lane and round, compacted into the fragment queue
-                    const uint32_t slot_bits = (uint32_t)slot << 12;
-                    for (int x = lo; __any_sync(0xffffffffu, x <= hi); x++) {
-                        const bool in = x <= hi;
-                        const uint32_t mi = __ballot_sync(0xffffffffu, in);
-                        if (in) fq[(fq_head + fq_n + __popc(mi & lt_mask)) & 63] = slot_bits | (pix_row + (uint32_t)x);
-                        fq_n += __popc(mi);
-                        __syncwarp();
-                        if (fq_n >= 32) drain(32);
+                    const uint32_t o_fnrec = __shfl_sync(0xffffffffu, fnrec, a);
+                    const uint32_t o_row = __shfl_sync(0xffffffffu, pix_row, a);
+                    const int o_lo = __shfl_sync(0xffffffffu, lo, a);
+                    if (i < nfrag) {
+                        const int pix = (int)o_row + o_lo + (i - spanpre[a]);
+                        const uint32_t rec = o_fnrec & 1023u;
+                        float inv[9], z[3];
+                        if (rec != kNoRec) {
+                            const float4* t4 = reinterpret_cast<const float4*>(sm.tab[rec]);
+                            const float4 aa = t4[0], bb = t4[1], cc = t4[2];
+                            inv[0] = aa.x; inv[1] = aa.y; inv[2] = aa.z; inv[3] = aa.w; inv[4] = bb.x; inv[5] = bb.y; inv[6] = bb.z;
+                            inv[7] = bb.w; inv[8] = cc.x; z[0] = cc.y; z[1] = cc.z; z[2] = cc.w;
+                        } else {
+                            face_record(p, b, (int)(o_fnrec >> 10), inv, z);  // tile with more than kTab survivors
+                        }
+                        const int lx = pix & (tw - 1), ly = pix >> p.tw_log2;
+                        float w[3];
+                        const float zp = nr::weights_and_depth(inv, (float)(tx0 + lx), (float)(ty0 + ly), z[0], z[1], z[2], w);
+                        // rasterize.py:331 + :334 against the initial depth_min = far; NaN fails both (never wins)
+                        if (zp > p.near_lo && zp < p.far_cmp) {
+                            const unsigned long long key = ((unsigned long long)nr::float_to_ordered(zp) << 32) | o_fnrec;
+                            unsigned long long* addr = zbuf + pix;
+                            if (key < *reinterpret_cast<volatile unsigned long long*>(addr)) atomicMin(addr, key);
+                        }
                     }
                 }
                 __syncwarp();
             }
-            ring_head = (ring_head + nsurv) & (kRing - 1);
+            __syncwarp();  // the scratch ring / prefix arrays are rewritten by the next group
         }
-        if (fq_n > 0) drain(fq_n);
     }
     __syncthreads();
 
