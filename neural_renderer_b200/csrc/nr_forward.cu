@@ -63,8 +63,9 @@ struct FwdParams {
 // ---------------------------------------------------------------------------------------------- k_raster_tile
 template <int kTL2, int kThreads>
 struct __align__(16) TileShared {
-    static constexpr int kTilePix = 1 << (2 * kTL2);
-    static constexpr int kTab = kTL2 >= 6 ? kTabMax : kTabMax / 2;
+    static constexpr int kTWL2 = kTL2 == 65 ? 6 : kTL2, kTHL2 = kTL2 == 65 ? 5 : kTL2;
+    static constexpr int kTilePix = 1 << (kTWL2 + kTHL2);
+    static constexpr int kTab = kTilePix >= 4096 ? kTabMax : kTabMax / 2;
     static constexpr int kWarps = kThreads / 32;
     unsigned long long zbuf[kTilePix];        // (ordered zp bits << 32 | face index << 10 | table slot), ~0 = empty
     float tab[kTab][kTabWords];               // survivor records {inv[9], z0, z1, z2} of this tile
@@ -141,7 +142,7 @@ __device__ __forceinline__ Shaded shade_pixel(const FwdParams& p, const float (*
 }
 
 template <bool kAA, int kTL2, int kThreads>
-__global__ void __launch_bounds__(kThreads) k_raster_tile(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(kThreads, kTL2 == 65 ? 1024 / kThreads : 1) k_raster_tile(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Shared = TileShared<kTL2, kThreads>;
     Shared& sm = *reinterpret_cast<Shared*>(smem_raw);
@@ -467,16 +468,18 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
     p.out_rgb = a->out_rgb; p.out_alpha = a->out_alpha; p.out_depth = a->out_depth;
     p.B = B; p.F = F; p.S = S; p.ts = ts; p.nchunks = nchunks;
     int tl = kFwdTileLog2Default, threads = kFwdThreadsDefault;  // tuning knobs: NR_B200_FWD_TILE (5|6), NR_B200_FWD_THREADS (128|256)
-    if (const char* env = getenv("NR_B200_FWD_TILE")) tl = atoi(env) <= 5 ? 5 : 6;
+    if (const char* env = getenv("NR_B200_FWD_TILE")) tl = atoi(env) <= 5 ? 5 : 6;  // 65 = 64 wide x 32 tall
     if (const char* env = getenv("NR_B200_FWD_THREADS")) threads = atoi(env) == 128 ? 128 : 256;
     // shrink the tile for small rasters so that it is not mostly padding (the kernels are compiled for 32 / 64 pixel
     // tiles; smaller rasters run the 32-pixel variant with the tile clipped to the image)
     while (tl > 3 && (1 << (tl - 1)) >= S) tl--;
     const int tile_log2 = tl;
     tl = tile_log2 >= 6 ? 6 : 5;
-    p.tw_log2 = tl; p.th_log2 = tl;
+    // default: 64 wide x 32 tall tiles (4 CTAs of 256 threads per SM); NR_B200_FWD_TILE=6 forces 64 x 64, 5 -> 32 x 32
+    const bool wide = (tl == 6) && !(getenv("NR_B200_FWD_TILE") && atoi(getenv("NR_B200_FWD_TILE")) == 6);
+    p.tw_log2 = tl; p.th_log2 = wide ? 5 : tl;
     p.tiles_x = (S + (1 << tl) - 1) >> tl;
-    const int tiles_y = p.tiles_x;
+    const int tiles_y = (S + (1 << p.th_log2) - 1) >> p.th_log2;
     p.flags = flags;
     p.near_lo = float_le(a->near_);
     p.far_cmp = fminf(float_ge(a->far_), (float)a->far_);
@@ -497,7 +500,10 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
         nr_internal::LaunchScope ls("k_raster_tile", stream);                                                              \
         k_raster_tile<AA, TL2, T><<<grid, T, smem, stream>>>(p);                                                           \
     } while (0)
-    if (tl >= 6) {
+    if (wide) {
+        if (threads == 128) { if (aa) NR_LAUNCH_TILE(true, 65, 128); else NR_LAUNCH_TILE(false, 65, 128); }
+        else                { if (aa) NR_LAUNCH_TILE(true, 65, 256); else NR_LAUNCH_TILE(false, 65, 256); }
+    } else if (tl >= 6) {
         if (threads == 128) { if (aa) NR_LAUNCH_TILE(true, 6, 128); else NR_LAUNCH_TILE(false, 6, 128); }
         else                { if (aa) NR_LAUNCH_TILE(true, 6, 256); else NR_LAUNCH_TILE(false, 6, 256); }
     } else {
