@@ -56,6 +56,7 @@ struct BwdParams {
     int W;          // lines per strip (power of two)
     int w_log2, nstrips;
     int len_shift;  // scan length >> len_shift -> one of 32 sort buckets
+    int debug_skip; // ablation knob (NR_B200_ES_SKIP): 1 = no in-scan, 2 = no out-scan, 4 = no task processing at all
     uint32_t flags;
     float eps, two_over_S, tex_cmp, tex_val;
 };
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
         Px q;
         q.c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         q.A = q.g0 = q.g1 = q.g2 = q.ga = 0.f;
-        if (d1 >= S) return q;  // the padding pixel of an odd raster size stays zero
+        if (d1 >= S || (p.debug_skip & 8)) return q;  // the padding pixel of an odd raster size stays zero
         const int x = (axis == 0) ? l0 + line : d1, y = (axis == 0) ? d1 : l0 + line;
         const int row = S - 1 - y;
         const size_t o = (size_t)row * S + x;
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
     const int* own = p.strip_list + __ldg(p.strip_off + cid + blockIdx.x);
     const int* wide = p.strip_list + __ldg(p.strip_off + cid + p.nstrips);
     const int ncand = n_own + n_wide;
-    for (int base = 0; base < ncand; base += kThreads) {
+    for (int base = 0; base < ncand && !(p.debug_skip & 16); base += kThreads) {
         // ---- 2a. this strip's faces (binned by k_strip_bin) plus the item's wide faces that overlap it
         const int i = base + tid;
         const bool last = base + kThreads >= ncand;
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                 int t0 = 0;
                 if (lane == 0) t0 = atomicAdd(&s_next, 32);
                 t0 = __shfl_sync(0xffffffffu, t0, 0);
-                if (t0 >= ntask) break;
+                if (t0 >= ntask || (p.debug_skip & 4)) break;
                 const int t = t0 + lane;
                 Task T;
                 T.valid = false; T.out_from = 0; T.out_to = -1; T.in_from = 0; T.in_to = -1;
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                     {   // in-scan (rasterize.py:662-730): reference colour = outside pixel, only pixels that show this face
                         const float4 cout = lci[T.d1_out];
                         const float ra = (kMode == 3) ? ((__float_as_int(cout.w) >= 0) ? 1.0f : 0.0f) : 0.0f;
-                        for (int d1 = T.in_from; d1 <= T.in_to; d1++) {
+                        for (int d1 = T.in_from; d1 <= T.in_to && !(p.debug_skip & 1); d1++) {
                             if (__float_as_int(lci[d1].w) != fn) continue;
                             visit(T, line, d1, cout.x, cout.y, cout.z, ra, acc0, acc1);
                         }
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                 // along an out-scan (d1 - d1_cross) keeps the sign of dir, so the sign of eps is fixed per vertex
                 const float fdir = (float)T.dir;
                 const float e0 = (fdir * T.k0 > 0.0f) ? p.eps : -p.eps, e1 = (fdir * T.k1 > 0.0f) ? p.eps : -p.eps;
-                const int my_from = fast ? T.out_from : 1, my_to = fast ? T.out_to : 0;
+                const int my_from = (fast && !(p.debug_skip & 2)) ? T.out_from : 1, my_to = (fast && !(p.debug_skip & 2)) ? T.out_to : 0;
                 float* gfb = p.grad_faces + ((size_t)b * p.F + fn) * 9 + (1 - axis);
                 const int qd = lane >> 2, j = lane & 3;  // 8 tasks per pass, 4 lanes (8 pixels per step) each
 #pragma unroll 1
@@ -721,6 +722,7 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
         const int W = L.W;
         p.W = W; p.w_log2 = L.w_log2; p.nstrips = L.nstrips;
         p.len_shift = 3;
+        p.debug_skip = getenv("NR_B200_ES_SKIP") ? atoi(getenv("NR_B200_ES_SKIP")) : 0;
         while ((2 * S) >> p.len_shift > 32) p.len_shift++;
         const size_t smem = (size_t)W * ((S + 1) & ~1) * rec_bytes;
         if (smem > 160 * 1024) return NR_ERR_UNSUPPORTED;

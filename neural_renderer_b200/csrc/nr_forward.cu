@@ -371,46 +371,32 @@ __global__ void __launch_bounds__(kThreads, kTL2 == 65 ? 1024 / kThreads : 1) k_
             const int lx = (q & ((1 << qw_log2) - 1)) << 1, ly = (q >> qw_log2) << 1;
             const int xi = tx0 + lx, yi = ty0 + ly;
             if (xi >= S || yi >= S) continue;  // S is even: quads are entirely in or out
-            // image-orientation quad: top row = raster row yi+1
-            const Shaded tl = shade_pixel(p, sm.tab, b, sm.zbuf[((ly + 1) << p.tw_log2) + lx], xi, yi + 1, bgr, bgg, bgb);
-            const Shaded tr = shade_pixel(p, sm.tab, b, sm.zbuf[((ly + 1) << p.tw_log2) + lx + 1], xi + 1, yi + 1, bgr, bgg, bgb);
-            const Shaded bl = shade_pixel(p, sm.tab, b, sm.zbuf[(ly << p.tw_log2) + lx], xi, yi, bgr, bgg, bgb);
-            const Shaded br = shade_pixel(p, sm.tab, b, sm.zbuf[(ly << p.tw_log2) + lx + 1], xi + 1, yi, bgr, bgg, bgb);
-            const size_t otop = (size_t)b * plane + (size_t)(S - 2 - yi) * S + xi;  // row of raster yi+1
-            const size_t obot = otop + S;
-            *reinterpret_cast<int2*>(p.fim + otop) = make_int2(tl.fim, tr.fim);
-            *reinterpret_cast<int2*>(p.fim + obot) = make_int2(bl.fim, br.fim);
-            *reinterpret_cast<float2*>(p.dmap + otop) = make_float2(tl.depth, tr.depth);
-            *reinterpret_cast<float2*>(p.dmap + obot) = make_float2(bl.depth, br.depth);
-            float* wt = p.wmap + (size_t)b * 3 * plane + (size_t)(S - 2 - yi) * S + xi;
-            *reinterpret_cast<float2*>(wt) = make_float2(tl.w0, tr.w0);
-            *reinterpret_cast<float2*>(wt + S) = make_float2(bl.w0, br.w0);
-            *reinterpret_cast<float2*>(wt + plane) = make_float2(tl.w1, tr.w1);
-            *reinterpret_cast<float2*>(wt + plane + S) = make_float2(bl.w1, br.w1);
-            *reinterpret_cast<float2*>(wt + 2 * plane) = make_float2(tl.w2, tr.w2);
-            *reinterpret_cast<float2*>(wt + 2 * plane + S) = make_float2(bl.w2, br.w2);
-            if (p.alpha) {
-                *reinterpret_cast<float2*>(p.alpha + otop) = make_float2(tl.alpha, tr.alpha);
-                *reinterpret_cast<float2*>(p.alpha + obot) = make_float2(bl.alpha, br.alpha);
+            // the four pixels are shaded one after the other (keeps the register footprint of a single pixel) in
+            // image order: top-left, top-right, bottom-left, bottom-right; top row = raster row yi + 1
+            float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f, sd = 0.f;
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) {
+                const int dx = k & 1, dy = 1 - (k >> 1);
+                const Shaded s = shade_pixel(p, sm.tab, b, sm.zbuf[((ly + dy) << p.tw_log2) + lx + dx], xi + dx, yi + dy, bgr, bgg, bgb);
+                const size_t o = (size_t)b * plane + (size_t)(S - 1 - (yi + dy)) * S + xi + dx;
+                p.fim[o] = s.fim;
+                p.dmap[o] = s.depth;
+                float* wm = p.wmap + (size_t)b * 3 * plane + (size_t)(S - 1 - (yi + dy)) * S + xi + dx;
+                wm[0] = s.w0; wm[plane] = s.w1; wm[2 * plane] = s.w2;
+                if (p.alpha) p.alpha[o] = s.alpha;
+                if (want_rgb) {
+                    float* rm = p.rgb + (size_t)b * 3 * plane + (size_t)(S - 1 - (yi + dy)) * S + xi + dx;
+                    rm[0] = s.r; rm[plane] = s.g; rm[2 * plane] = s.b;
+                }
+                sr += s.r; sg += s.g; sb += s.b; sa += s.alpha; sd += s.depth;
             }
             const size_t oo = (size_t)(H - 1 - (yi >> 1)) * H + (xi >> 1);
-            if (want_rgb) {
-                float* rt = p.rgb + (size_t)b * 3 * plane + (size_t)(S - 2 - yi) * S + xi;
-                *reinterpret_cast<float2*>(rt) = make_float2(tl.r, tr.r);
-                *reinterpret_cast<float2*>(rt + S) = make_float2(bl.r, br.r);
-                *reinterpret_cast<float2*>(rt + plane) = make_float2(tl.g, tr.g);
-                *reinterpret_cast<float2*>(rt + plane + S) = make_float2(bl.g, br.g);
-                *reinterpret_cast<float2*>(rt + 2 * plane) = make_float2(tl.b, tr.b);
-                *reinterpret_cast<float2*>(rt + 2 * plane + S) = make_float2(bl.b, br.b);
-                if (p.out_rgb) {
-                    float* orgb = p.out_rgb + (size_t)b * 3 * oplane + oo;
-                    orgb[0] = (((tl.r + tr.r) + bl.r) + br.r) * 0.25f;
-                    orgb[oplane] = (((tl.g + tr.g) + bl.g) + br.g) * 0.25f;
-                    orgb[2 * oplane] = (((tl.b + tr.b) + bl.b) + br.b) * 0.25f;
-                }
+            if (want_rgb && p.out_rgb) {
+                float* orgb = p.out_rgb + (size_t)b * 3 * oplane + oo;
+                orgb[0] = sr * 0.25f; orgb[oplane] = sg * 0.25f; orgb[2 * oplane] = sb * 0.25f;
             }
-            if (p.out_alpha) p.out_alpha[(size_t)b * oplane + oo] = (((tl.alpha + tr.alpha) + bl.alpha) + br.alpha) * 0.25f;
-            if (p.out_depth) p.out_depth[(size_t)b * oplane + oo] = (((tl.depth + tr.depth) + bl.depth) + br.depth) * 0.25f;
+            if (p.out_alpha) p.out_alpha[(size_t)b * oplane + oo] = sa * 0.25f;
+            if (p.out_depth) p.out_depth[(size_t)b * oplane + oo] = sd * 0.25f;
         }
     }
 }
