@@ -7,18 +7,24 @@
 //
 //   k_face_bbox   one thread per face: back-face / non-finite cull and a conservative pixel bounding box
 //                 (8 bytes per face) plus one union box per 256-face chunk -- the only scratch the pass needs.
-//   k_raster_tile one CTA per 64x64 screen tile (the z-tile lives in shared memory as 64-bit (zp, face) keys):
-//                   1. warps pull 32-face groups, cull them against the tile by chunk box then face box,
-//                   2. survivors get their exact K1 inverse computed once (lane-parallel) into a per-warp ring,
-//                   3. each survivor's clipped box is swept 8x4 pixels at a time with the reference's three
-//                      edge tests; passing (face, pixel) fragments are warp-compacted into a per-warp queue,
-//                   4. full warps of fragments evaluate the exact barycentric / perspective-depth expression and
-//                      min-reduce (ordered zp bits << 32 | face index) into the z-tile -- lexicographic
-//                      (zp, fn) minimum == the reference's strict `<` over ascending face index,
-//                   5. after one barrier every thread resolves pixels: recompute the winner's weights with the
-//                      same expression tree, sample its ts^3 texture (K4), composite the background, and stream
-//                      all maps out as planar, row-flipped (image orientation) coalesced rows; with
-//                      anti-aliasing each thread owns a 2x2 quad and also emits the pooled API pixel.
+//   k_raster_tile one CTA per 64x32 screen tile (the z-tile lives in shared memory as 64-bit keys
+//                 ordered-zp << 32 | face << 10 | record slot):
+//                   1. warps pull 32-face groups and cull them against the tile by chunk box, then face box;
+//                   2. survivors (one per lane) get their exact K1 inverse computed once into a per-tile record
+//                      table {inv[9], z[3]} and a small sweep record (vertices, clipped box);
+//                   3. row-span rasterization: for a fixed pixel row every edge test of the reference,
+//                      r_k < (xp - x_k) * dy_k, is monotone in x, so the covered pixels of a row form one interval
+//                      whose ends are found by binary search WITH THE REFERENCE'S OWN EXPRESSIONS (identical
+//                      coverage, O(log width) tests per row).  Lanes = rows of the group's survivors, flattened
+//                      over faces, 32 rows per pass;
+//                   4. the pixels of the 32 spans are flattened again (prefix sum) and evaluated 32 fragments at a
+//                      time: exact barycentric / perspective-depth expression, then a shared-memory 64-bit min --
+//                      lexicographic (zp, fn) minimum == the reference's strict `<` over ascending face index;
+//                   5. after one barrier every thread resolves pixels: the winner's record comes from the table
+//                      (weights re-evaluated with the same expression tree), its ts^3 texture is sampled (K4), the
+//                      background composited, and all maps are streamed out as planar, row-flipped (image
+//                      orientation) coalesced rows; with anti-aliasing each thread owns a 2x2 quad and also emits
+//                      the pooled API pixel.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
