@@ -385,6 +385,19 @@ def test_vertices_to_faces_kernels(teapot):
     assert rel_err(np_(vert.grad), np_(ref_in.grad)) <= 1e-5
 
 
+def test_examples_optimise():
+    """The reference's example 2 / 3 call sequences (torch instead of Chainer) make progress end to end."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name, iters in (("example2_optimize_vertices", 30), ("example3_optimize_textures", 15)):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, "examples", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        losses = mod.run(iters)
+        assert np.isfinite(losses).all() and losses[-1] < 0.8 * losses[0], (name, losses[0], losses[-1])
+
+
 def test_edge_cases():
     """Empty / degenerate inputs the reference's tests exercise implicitly (all-zero batch slots of to_minibatch),
     single face, faces entirely off screen, rgb + per-batch background."""
