@@ -385,6 +385,42 @@ def test_vertices_to_faces_kernels(teapot):
     assert rel_err(np_(vert.grad), np_(ref_in.grad)) <= 1e-5
 
 
+def test_cuda_graph_capture_and_side_stream():
+    """The C ABI only enqueues work on the caller's stream (no hidden allocation or synchronisation), so a forward +
+    backward pass can run on a side stream and be captured in a CUDA graph and replayed."""
+    import neural_renderer as nr
+    faces_np, tex_np = _inputs("sphere", 2, 200, 2, seed=5)
+    dev = torch.device("cuda")
+    faces = torch.from_numpy(faces_np).to(dev).requires_grad_(True)
+    tex = torch.from_numpy(tex_np).to(dev).requires_grad_(True)
+    g = torch.randn((2, 3, 64, 64), generator=torch.Generator().manual_seed(1)).to(dev)
+
+    def step():
+        faces.grad = None
+        tex.grad = None
+        img = nr.rasterize(faces, tex, 64, False)
+        img.backward(g)
+        return img.detach().clone(), faces.grad.clone(), tex.grad.clone()
+
+    ref = step()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):  # warm-up on the side stream (allocator, autograd engine)
+            on_side = step()
+    torch.cuda.current_stream().wait_stream(side)
+    assert torch.equal(on_side[0], ref[0]) and rel_err(np_(on_side[1]), np_(ref[1])) <= 1e-5
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = step()
+    for t in out:
+        t.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], ref[0])
+    assert rel_err(np_(out[1]), np_(ref[1])) <= 1e-5 and rel_err(np_(out[2]), np_(ref[2])) <= 1e-5
+
+
 def test_examples_optimise():
     """The reference's example 2 / 3 call sequences (torch instead of Chainer) make progress end to end."""
     import importlib.util
