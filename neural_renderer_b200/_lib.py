@@ -9,7 +9,7 @@ import ctypes
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libnr_b200.so")
+LIB_PATH = os.environ.get("NR_B200_LIB", os.path.join(PKG_DIR, "libnr_b200.so"))  # override: kernel A/B experiments
 
 NR_OK = 0
 NR_RETURN_RGB = 1

@@ -45,9 +45,10 @@ def is_stale():
     return any(os.path.getmtime(f) > t for f in _deps() if os.path.exists(f))
 
 
-def build_library(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into neural_renderer_b200/libnr_b200.so."""
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """Compile every CUDA source for sm_100a into neural_renderer_b200/libnr_b200.so (`defines` / `out`: experiment
+    builds with extra -D flags into another file, selected at run time with NR_B200_LIB)."""
+    if out is None and not force and not is_stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     objs = []
@@ -55,21 +56,23 @@ def build_library(force=False, verbose=False):
     build_dir = os.path.join(PKG_DIR, "build")
     os.makedirs(build_dir, exist_ok=True)
     for src in _sources():
-        obj = os.path.join(build_dir, os.path.basename(src) + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        tag = ("." + "_".join(defines).replace("=", "-")) if defines else ""
+        obj = os.path.join(build_dir, os.path.basename(src) + tag + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if verbose or p.returncode != 0:
-            sys.stderr.write(out)
+            sys.stderr.write(log)
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    target = out or LIB_PATH
+    cmd = [nvcc, "-shared", "-o", target] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     subprocess.run(cmd, check=True)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":

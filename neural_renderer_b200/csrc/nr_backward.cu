@@ -478,6 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                         const float ta = __fsub_rn((float)(pp << 1), o_dc);
                         f32x2 tt2 = pk(ta, ta + 1.0f);  // (d1 - d1_cross) of the lane's two pixels; +8 per step
                         const f32x2 step2 = pk(8.0f, 8.0f), one2 = pk(1.0f, 1.0f);
+#pragma unroll 2  // measured: 2 beats the compiler's default (4) and 1
                         for (; pp <= pb; pp += 4) {
                             const float4 pv = P[lb + pp];
                             f32x2 dg2 = fma2(nc0, pk(pv.z, pv.w), pk(pv.x, pv.y));
