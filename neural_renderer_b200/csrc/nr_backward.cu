@@ -164,6 +164,7 @@ typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void upk(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 // Shared-memory strip.  Pixels of a line are stored as PAIRS (2*pp, 2*pp+1) so that one 16-byte load feeds one packed
@@ -467,44 +468,66 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                     const float o_c0 = __shfl_sync(0xffffffffu, c0, src), o_c1 = __shfl_sync(0xffffffffu, c1, src);
                     const float o_c2 = __shfl_sync(0xffffffffu, c2, src);
                     const float o_ca = (kMode == 3) ? __shfl_sync(0xffffffffu, ca, src) : 0.0f;
+                    const int o_dir = __shfl_sync(0xffffffffu, T.dir, src);
                     if (!__any_sync(0xffffffffu, o_from <= o_to)) continue;
-                    f32x2 a0 = pk(0.f, 0.f), a1 = pk(0.f, 0.f);
-                    if (o_from <= o_to) {
+                    f32x2 a0 = pk(0.f, 0.f), a1 = pk(0.f, 0.f);  // positive sums; the sign is applied at the hand-over
+                    // An out-scan runs from the crossing to an image border, so only the pixel pair at the crossing end
+                    // can hold a pixel outside [o_from, o_to] (the padding pixel of an odd raster size is staged as
+                    // zeros).  Pairs are therefore walked FROM the crossing: the first step is peeled with the range
+                    // gates, the steady-state loop carries none.
+                    const int pa = o_from >> 1, npairs = (o_to >> 1) - pa + 1;
+                    if (o_from <= o_to && j < npairs) {
+                        const bool up = o_dir > 0;
                         const f32x2 nc0 = pk(-o_c0, -o_c0), nc1 = pk(-o_c1, -o_c1), nc2 = pk(-o_c2, -o_c2), nca = pk(-o_ca, -o_ca);
-                        const f32x2 k0_2 = pk(o_k0, o_k0), k1_2 = pk(o_k1, o_k1), e0_2 = pk(o_e0, o_e0), e1_2 = pk(o_e1, o_e1);
-                        const size_t lb = (size_t)o_line * npair;
-                        const int pb = o_to >> 1;
-                        int pp = (o_from >> 1) + j;
-                        const float ta = __fsub_rn((float)(pp << 1), o_dc);
-                        f32x2 tt2 = pk(ta, ta + 1.0f);  // (d1 - d1_cross) of the lane's two pixels; +8 per step
-                        const f32x2 step2 = pk(8.0f, 8.0f), one2 = pk(1.0f, 1.0f);
-#pragma unroll 2  // measured: 2 beats the compiler's default (4) and 1
-                        for (; pp <= pb; pp += 4) {
-                            const float4 pv = P[lb + pp];
+                        int pp = up ? pa + j : (o_to >> 1) - j;
+                        const float4* Pp = P + (size_t)o_line * npair + pp;
+                        const float4* Qp = Q + (size_t)o_line * npair + pp;
+                        const float2* Rp = R + (size_t)o_line * npair + pp;
+                        const int dpp = up ? 4 : -4;
+                        const float ta = __fsub_rn((float)(pp << 1), o_dc);  // d1 - d1_cross of the lane's first pixel
+                        const f32x2 tt2 = pk(ta, ta + 1.0f);
+                        // dist_v = (d1 - d1_cross) * k_v +- eps, advanced by +-8 pixels per step
+                        f32x2 d0_2 = fma2(tt2, pk(o_k0, o_k0), pk(o_e0, o_e0)), d1_2 = fma2(tt2, pk(o_k1, o_k1), pk(o_e1, o_e1));
+                        const float s8 = up ? 8.0f : -8.0f;
+                        const f32x2 dk0 = pk(s8 * o_k0, s8 * o_k0), dk1 = pk(s8 * o_k1, s8 * o_k1);
+                        auto diff_grad = [&](float& dga, float& dgb) {
+                            const float4 pv = *Pp;
                             f32x2 dg2 = fma2(nc0, pk(pv.z, pv.w), pk(pv.x, pv.y));
                             if (kMode != 2) {
-                                const float4 qv = Q[lb + pp];
+                                const float4 qv = *Qp;
                                 dg2 = fma2(nc1, pk(qv.x, qv.y), dg2);
                                 dg2 = fma2(nc2, pk(qv.z, qv.w), dg2);
                             }
                             if (kMode == 3) {
-                                const float2 rv = R[lb + pp];
+                                const float2 rv = *Rp;
                                 dg2 = fma2(nca, pk(rv.x, rv.y), dg2);
                             }
-                            float dga, dgb;
                             upk(dg2, dga, dgb);
-                            const int y0 = pp << 1;
-                            // relu gate of rasterize.py:647 (max drops a NaN diff_grad) and the ends of the scan range
-                            dga = (y0 >= o_from) ? fmaxf(dga, 0.0f) : 0.0f;
-                            dgb = (y0 + 1 <= o_to) ? fmaxf(dgb, 0.0f) : 0.0f;
-                            const f32x2 d0_2 = fma2(tt2, k0_2, e0_2), d1_2 = fma2(tt2, k1_2, e1_2);
-                            tt2 = fma2(step2, one2, tt2);
-                            float pa, pb2;
-                            upk(mul2(d0_2, d1_2), pa, pb2);
+                        };
+                        auto accumulate = [&](float dga, float dgb) {
+                            float qa, qb;
+                            upk(mul2(d0_2, d1_2), qa, qb);
                             // one reciprocal serves both vertices: dg / d0 = dg * d1 / (d0 * d1)
-                            const f32x2 t2 = mul2(pk(-dga, -dgb), pk(rcp_approx(pa), rcp_approx(pb2)));
+                            const f32x2 t2 = mul2(pk(dga, dgb), pk(rcp_approx(qa), rcp_approx(qb)));
                             a0 = fma2(t2, d1_2, a0);
                             a1 = fma2(t2, d0_2, a1);
+                            d0_2 = add2(d0_2, dk0);
+                            d1_2 = add2(d1_2, dk1);
+                            Pp += dpp; Qp += dpp; Rp += dpp;
+                        };
+                        {   // first step: relu gate of rasterize.py:647 (max drops a NaN diff_grad) + range ends
+                            float dga, dgb;
+                            diff_grad(dga, dgb);
+                            const int y0 = pp << 1;
+                            dga = (y0 >= o_from) ? fmaxf(dga, 0.0f) : 0.0f;
+                            dgb = (y0 + 1 <= o_to) ? fmaxf(dgb, 0.0f) : 0.0f;
+                            accumulate(dga, dgb);
+                        }
+#pragma unroll 2
+                        for (int i = j + 4; i < npairs; i += 4) {
+                            float dga, dgb;
+                            diff_grad(dga, dgb);
+                            accumulate(fmaxf(dga, 0.0f), fmaxf(dgb, 0.0f));
                         }
                     }
                     float s0a, s0b, s1a, s1b;
@@ -518,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                     }
                     // hand the totals to the lane that owns the task
                     const float r0 = __shfl_sync(0xffffffffu, s0, (lane & 7) << 2), r1 = __shfl_sync(0xffffffffu, s1, (lane & 7) << 2);
-                    if ((lane >> 3) == sub) { acc0 += r0; acc1 += r1; }
+                    if ((lane >> 3) == sub) { acc0 -= r0; acc1 -= r1; }
                 }
                 if (acc0 != 0.0f) atomicAdd(gfb + 3 * T.pi0, acc0);
                 if (acc1 != 0.0f) atomicAdd(gfb + 3 * T.pi1, acc1);
