@@ -601,38 +601,62 @@ __global__ void __launch_bounds__(256) k_depth_grad(const __grid_constant__ BwdP
     const size_t plane = (size_t)S * S;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
-    if (i >= plane) return;
-    const int fn = __ldg(p.fim + (size_t)b * plane + i);
-    if (fn < 0) return;
-    const int row = (int)(i / S), col = (int)(i % S);
-    const bool aa = (p.flags & NR_ANTI_ALIASING) != 0;
-    const float g = load_grad(p.g_depth, aa, S, (size_t)b, row, col);
-    const float* v = p.faces + ((size_t)b * p.F + fn) * 9;
-    float c[9];
+    const int lane = threadIdx.x & 31;
+    const int fn = (i < plane) ? __ldg(p.fim + (size_t)b * plane + i) : -1;
+    float out[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) c[k] = __ldg(v + k);
-    const float fS = (float)S;
-    float inv[9];
-    nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS), nr::to_pixel(c[4], fS),
-                     nr::to_pixel(c[6], fS), nr::to_pixel(c[7], fS), inv);
-    const float* wm = p.wmap + (size_t)b * 3 * plane + i;
-    const float w[3] = {__ldg(wm), __ldg(wm + plane), __ldg(wm + 2 * plane)};
-    const float depth = __ldg(p.dmap + (size_t)b * plane + i);
-    const float depth2 = depth * depth;
-    const float z[3] = {c[2], c[5], c[8]};
-    float* gf = p.grad_faces + ((size_t)b * p.F + fn) * 9;
-    // rasterize.py:824-827  d zp / d z_k = w_k * zp^2 / z_k^2
+    for (int k = 0; k < 9; k++) out[k] = 0.0f;
+    if (fn >= 0) {
+        const int row = (int)(i / S), col = (int)(i % S);
+        const bool aa = (p.flags & NR_ANTI_ALIASING) != 0;
+        const float g = load_grad(p.g_depth, aa, S, (size_t)b, row, col);
+        const float* v = p.faces + ((size_t)b * p.F + fn) * 9;
+        float c[9];
 #pragma unroll
-    for (int k = 0; k < 3; k++) atomicAdd(gf + 3 * k + 2, __fdiv_rn((g * w[k]) * depth2, z[k] * z[k]));
-    // rasterize.py:830-837  tmp_l = -sum_v inv[v][l] / z_v ;  d zp / d (x,y)_k = -g * tmp_l * w_k * zp^2 * is / 2
-    float tmp[2];
+        for (int k = 0; k < 9; k++) c[k] = __ldg(v + k);
+        const float fS = (float)S;
+        float inv[9];
+        nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS), nr::to_pixel(c[4], fS),
+                         nr::to_pixel(c[6], fS), nr::to_pixel(c[7], fS), inv);
+        const float* wm = p.wmap + (size_t)b * 3 * plane + i;
+        const float w[3] = {__ldg(wm), __ldg(wm + plane), __ldg(wm + 2 * plane)};
+        const float depth = __ldg(p.dmap + (size_t)b * plane + i);
+        const float depth2 = depth * depth;
+        const float z[3] = {c[2], c[5], c[8]};
+        // rasterize.py:824-827  d zp / d z_k = w_k * zp^2 / z_k^2
 #pragma unroll
-    for (int l = 0; l < 2; l++)
-        tmp[l] = ((0.0f - __fdiv_rn(inv[l], z[0])) - __fdiv_rn(inv[3 + l], z[1])) - __fdiv_rn(inv[6 + l], z[2]);
+        for (int k = 0; k < 3; k++) out[3 * k + 2] = __fdiv_rn((g * w[k]) * depth2, z[k] * z[k]);
+        // rasterize.py:830-837  tmp_l = -sum_v inv[v][l] / z_v ;  d zp / d (x,y)_k = -g * tmp_l * w_k * zp^2 * is / 2
+        float tmp[2];
 #pragma unroll
-    for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 2; l++)
+            tmp[l] = ((0.0f - __fdiv_rn(inv[l], z[0])) - __fdiv_rn(inv[3 + l], z[1])) - __fdiv_rn(inv[6 + l], z[2]);
 #pragma unroll
-        for (int l = 0; l < 2; l++) atomicAdd(gf + 3 * k + l, (((((-g) * tmp[l]) * w[k]) * depth2) * fS) * 0.5f);
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int l = 0; l < 2; l++) out[3 * k + l] = (((((-g) * tmp[l]) * w[k]) * depth2) * fS) * 0.5f;
+    }
+    // Warp-aggregated scatter: a warp holds 32 consecutive pixels of a row, where a (convex) face shows as a run of
+    // neighbouring lanes.  Each run is summed with a segmented shuffle reduction and its first lane issues the nine
+    // atomics (the reference issues them per pixel, rasterize.py:826-837; fp32 atomics are unordered there too).
+    const int fn_prev = __shfl_up_sync(0xffffffffu, fn, 1);
+    const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || fn != fn_prev);
+    const uint32_t later = heads & ~((2u << lane) - 1u);  // run heads after this lane (2u << 31 wraps to 0: mask = all)
+    const int run_end = (lane == 31 || later == 0) ? 31 : (__ffs(later) - 2);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const bool take = lane + off <= run_end;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const float t = __shfl_down_sync(0xffffffffu, out[k], off);
+            if (take) out[k] += t;
+        }
+    }
+    if (fn >= 0 && ((heads >> lane) & 1u)) {
+        float* gf = p.grad_faces + ((size_t)b * p.F + fn) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; k++) atomicAdd(gf + k, out[k]);
+    }
 }
 
 inline float float_le(double d) {
@@ -732,14 +756,14 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
     // K5 runs when an rgb or alpha gradient exists (rasterize.py:523); without upstream gradients it contributes 0
     const bool need_scan = (rgb && p.g_rgb) || (alpha && p.g_alpha);
     if (need_scan) {
-        const int nchunks = (F + kChunk - 1) / kChunk;
+        const int nchunks = (F + kChunk - 1) / kChunk, ngroups = (F + kGroup - 1) / kGroup;
         uint2* bbox = (uint2*)a->workspace;
         uint2* cbox = (uint2*)((char*)a->workspace + nr_align_up((size_t)B * F * sizeof(uint2), 256));
         {
             nr_internal::LaunchScope ls("k_face_bbox", stream);
-            k_face_bbox<<<dim3(nchunks, B), kChunk, 0, stream>>>(a->faces, F, S, nchunks, bbox, cbox);
+            k_face_bbox<<<dim3(nchunks, B), kChunk, 0, stream>>>(a->faces, F, S, ngroups, bbox, cbox);
         }
-        p.bbox = bbox; p.chunk_bbox = cbox; p.nchunks = nchunks;
+        p.bbox = bbox; p.chunk_bbox = cbox; p.nchunks = ngroups;
         const bool use_rgb = rgb && p.g_rgb, use_alpha = alpha && p.g_alpha;
         const int rec_bytes = (use_rgb && use_alpha) ? 36 : 32;
         const BinLayout L = bin_layout(B, F, S, (rgb && alpha) ? 36 : 32);  // same strip width as the workspace query

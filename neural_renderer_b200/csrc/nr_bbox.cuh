@@ -3,8 +3,8 @@
 // k_face_bbox: one thread per face.  Back faces (rasterize.py:252/:306/:540) and faces with a non-finite x/y (they
 // can never win a pixel: their barycentric weights clamp to 0 and zp becomes NaN) get an empty box; every other
 // face gets a conservative pixel box (8 bytes) that contains every pixel centre the reference's edge tests can
-// accept and every column/row its edge scan can start from.  One union box per 256-face chunk lets consumers skip
-// whole chunks.  This is the only per-face scratch either pass needs.
+// accept and every column/row its edge scan can start from.  One union box per group of 32 consecutive faces (a warp
+// of this kernel) lets the forward tiles skip whole groups.  This is the only per-face scratch either pass needs.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -13,7 +13,8 @@
 
 namespace {
 
-constexpr int kChunk = 256;  // faces per chunk box == threads of k_face_bbox
+constexpr int kChunk = 256;  // threads (faces) per CTA of k_face_bbox
+constexpr int kGroup = 32;   // faces per group box: the unit the forward tiles cull and pull
 constexpr float kBoxMargin = 1.0f / 256.0f;  // pixels; covers fp32 slack of to_pixel and of the edge tests
 
 __device__ __forceinline__ int unpack_lo(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
@@ -21,8 +22,8 @@ __device__ __forceinline__ int unpack_hi(uint32_t v) { return (int)(short)(v >> 
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 
 // ------------------------------------------------------------------------------------------------ k_face_bbox
-__global__ void __launch_bounds__(kChunk) k_face_bbox(const float* __restrict__ faces, int F, int S, int nchunks,
-                                                      uint2* __restrict__ bbox, uint2* __restrict__ chunk_bbox) {
+__global__ void __launch_bounds__(kChunk) k_face_bbox(const float* __restrict__ faces, int F, int S, int ngroups,
+                                                      uint2* __restrict__ bbox, uint2* __restrict__ group_bbox) {
     const int b = blockIdx.y;
     const int f = blockIdx.x * kChunk + threadIdx.x;
     int xlo = 1, xhi = 0, ylo = 1, yhi = 0;  // empty
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(kChunk) k_face_bbox(const float* __restrict__ 
         }
         bbox[(size_t)b * F + f] = make_uint2(pack16(xlo, xhi), pack16(ylo, yhi));
     }
-    // union box of the chunk (empty faces do not contribute)
+    // union box of the warp's 32 faces (empty faces do not contribute; an all-empty group gets an empty box)
     const bool ne = xlo <= xhi;
     int cxlo = ne ? xlo : 32767, cxhi = ne ? xhi : -1, cylo = ne ? ylo : 32767, cyhi = ne ? yhi : -1;
 #pragma unroll
@@ -55,28 +56,19 @@ __global__ void __launch_bounds__(kChunk) k_face_bbox(const float* __restrict__ 
         cylo = min(cylo, __shfl_xor_sync(0xffffffffu, cylo, o));
         cyhi = max(cyhi, __shfl_xor_sync(0xffffffffu, cyhi, o));
     }
-    __shared__ int red[4][kChunk / 32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { red[0][warp] = cxlo; red[1][warp] = cxhi; red[2][warp] = cylo; red[3][warp] = cyhi; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int w = 1; w < kChunk / 32; w++) {
-            cxlo = min(cxlo, red[0][w]); cxhi = max(cxhi, red[1][w]);
-            cylo = min(cylo, red[2][w]); cyhi = max(cyhi, red[3][w]);
-        }
-        chunk_bbox[(size_t)b * nchunks + blockIdx.x] = make_uint2(pack16(cxlo, cxhi), pack16(cylo, cyhi));
-    }
+    const int g = (blockIdx.x * kChunk + threadIdx.x) >> 5;
+    if ((threadIdx.x & 31) == 0 && g < ngroups)
+        group_bbox[(size_t)b * ngroups + g] = make_uint2(pack16(cxlo, cxhi), pack16(cylo, cyhi));
 }
 
 
 inline size_t nr_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// workspace layout used by both passes: [B*F] face boxes, then [B*nchunks] chunk boxes
+// workspace layout used by both passes: [B*F] face boxes, then [B*ngroups] group boxes
 inline size_t bbox_workspace_bytes(int B, int F) {
     if (B <= 0 || F <= 0) return 16;
-    const size_t nchunks = ((size_t)F + kChunk - 1) / kChunk;
-    return nr_align_up((size_t)B * F * sizeof(uint2), 256) + nr_align_up((size_t)B * nchunks * sizeof(uint2), 256);
+    const size_t ngroups = ((size_t)F + kGroup - 1) / kGroup;
+    return nr_align_up((size_t)B * F * sizeof(uint2), 256) + nr_align_up((size_t)B * ngroups * sizeof(uint2), 256);
 }
 
 }  // namespace

@@ -6,10 +6,12 @@
 // The reference tests every face against every pixel (B*S*S*F face tests).  Here:
 //
 //   k_face_bbox   one thread per face: back-face / non-finite cull and a conservative pixel bounding box
-//                 (8 bytes per face) plus one union box per 256-face chunk -- the only scratch the pass needs.
+//                 (8 bytes per face) plus one union box per group of 32 consecutive faces -- the only scratch the
+//                 pass needs.
 //   k_raster_tile one CTA per 64x32 screen tile (the z-tile lives in shared memory as 64-bit keys
 //                 ordered-zp << 32 | face << 10 | record slot):
-//                   1. warps pull 32-face groups and cull them against the tile by chunk box, then face box;
+//                   1. every thread culls one 32-face group box against the tile (the survivors' indices are queued
+//                      in shared memory); warps then pull queued groups and cull their faces by face box;
 //                   2. survivors (one per lane) get their exact K1 inverse computed once into a per-tile record
 //                      table {inv[9], z[3]} and a small sweep record (vertices, clipped box);
 //                   3. row-span rasterization: for a fixed pixel row every edge test of the reference,
@@ -43,6 +45,7 @@ constexpr int kRingWords = 8;
 constexpr int kFwdTileLog2Default = 6, kFwdThreadsDefault = 256;
 constexpr int kTabMax = 512;   // per-tile table of survivor records {inv[9], z[3]} that fragments and the shade pass share
 constexpr int kTabWords = 12;
+constexpr int kLiveCap = 1024;  // groups culled against the tile per pass (the survivors' indices are queued in smem)
 constexpr uint32_t kNoRec = 1023;  // z-keys carry (face index << 10 | table slot); 1023 = "not in the table"
 
 struct FwdParams {
@@ -50,7 +53,7 @@ struct FwdParams {
     const float* textures;
     const float* bg_batch;
     const uint2* bbox;
-    const uint2* chunk_bbox;
+    const uint2* group_bbox;
     int32_t* fim;
     float* wmap;
     float* dmap;
@@ -59,7 +62,7 @@ struct FwdParams {
     float* out_rgb;
     float* out_alpha;
     float* out_depth;
-    int B, F, S, ts, nchunks;
+    int B, F, S, ts, ngroups;
     int tw_log2, th_log2, tiles_x;
     uint32_t flags;
     float near_lo, far_cmp, far_val, tex_cmp, tex_val;
@@ -80,6 +83,8 @@ struct __align__(16) TileShared {
     float yp[64];
     int rowpre[kWarps][32];                   // per-warp: first row number of each survivor of the current group
     int spanpre[kWarps][32];                  // per-warp: first fragment number of each row span of the current pass
+    int live[kLiveCap];                       // groups of the current pass whose box overlaps the tile
+    int live_count;
     int next_group;
     int tab_count;
 };
@@ -169,30 +174,51 @@ __global__ void __launch_bounds__(kThreads, kTL2 == 65 ? 1024 / kThreads : 1) k_
         sm.xp[tid] = (float)((double)(2 * (tx0 + tid) + 1 - p.S) / dS);
         sm.yp[tid] = (float)((double)(2 * (ty0 + tid) + 1 - p.S) / dS);
     }
-    if (tid == 0) { sm.next_group = 0; sm.tab_count = 0; }
-    __syncthreads();
+    if (tid == 0) sm.tab_count = 0;
 
-    // ------------------------------------------------------------------ raster phase (warp-autonomous)
-    {
-        const int ngroups = (p.F + 31) >> 5;
+    // ------------------------------------------------------------------ raster phase
+    const int ngroups = p.ngroups;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int gbase = 0; gbase < ngroups; gbase += kLiveCap) {
+        // ---- group cull, one group (32 consecutive faces) per thread: the groups whose union box overlaps the tile
+        //      are queued in shared memory, so the warps below only ever touch faces near the tile
+        if (tid == 0) { sm.live_count = 0; sm.next_group = 0; }
+        __syncthreads();
+        {
+            const uint2* gbox = p.group_bbox + (size_t)b * ngroups;
+            const int gend = min(gbase + kLiveCap, ngroups);
+            for (int g0 = gbase + (warp << 5); g0 < gend; g0 += kThreads) {  // warp-uniform trip count
+                const int g = g0 + lane;
+                bool hit = false;
+                if (g < gend) {
+                    const uint2 cb = __ldg(gbox + g);
+                    hit = !(unpack_lo(cb.x) > tx1 || unpack_hi(cb.x) < tx0 || unpack_lo(cb.y) > ty1 || unpack_hi(cb.y) < ty0);
+                }
+                const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+                if (hm != 0u) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&sm.live_count, __popc(hm));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (hit) sm.live[base + __popc(hm & lt_mask)] = g;
+                }
+            }
+        }
+        __syncthreads();
+        const int nlive = sm.live_count;
+        // ---- warp-autonomous: pull live groups
         const uint2* bbox = p.bbox + (size_t)b * p.F;
-        const uint2* cbox = p.chunk_bbox + (size_t)b * p.nchunks;
         float(*ring)[kRingWords] = sm.ring[warp];
         int* rowpre = sm.rowpre[warp];
         int* spanpre = sm.spanpre[warp];
         unsigned long long* zbuf = sm.zbuf;
         const float fS = (float)p.S;
-        const uint32_t lt_mask = (1u << lane) - 1u;
 
         while (true) {
-            int g = 0;
-            if (lane == 0) g = atomicAdd(&sm.next_group, 1);
-            g = __shfl_sync(0xffffffffu, g, 0);
-            if (g >= ngroups) break;
-            {   // chunk-level cull (uniform)
-                const uint2 cb = __ldg(cbox + (g >> 3));
-                if (unpack_lo(cb.x) > tx1 || unpack_hi(cb.x) < tx0 || unpack_lo(cb.y) > ty1 || unpack_hi(cb.y) < ty0) continue;
-            }
+            int gi = 0;
+            if (lane == 0) gi = atomicAdd(&sm.next_group, 1);
+            gi = __shfl_sync(0xffffffffu, gi, 0);
+            if (gi >= nlive) break;
+            const int g = sm.live[gi];
             const int f = (g << 5) + lane;
             bool pass = false;
             int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
@@ -340,8 +366,8 @@ __global__ void __launch_bounds__(kThreads, kTL2 == 65 ? 1024 / kThreads : 1) k_
             }
             __syncwarp();  // the scratch ring / prefix arrays are rewritten by the next group
         }
+        __syncthreads();  // every fragment of this pass is in the z-tile; the group queue may be rebuilt
     }
-    __syncthreads();
 
     // ------------------------------------------------------------------ resolve + shade + stream out
     const int S = p.S;
@@ -444,21 +470,21 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
     if (!a->workspace || a->workspace_bytes < need || ((uintptr_t)a->workspace & 15)) return NR_ERR_WORKSPACE;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
 
-    const int nchunks = (F + kChunk - 1) / kChunk;
+    const int nchunks = (F + kChunk - 1) / kChunk, ngroups = (F + kGroup - 1) / kGroup;
     uint2* bbox = (uint2*)a->workspace;
     uint2* cbox = (uint2*)((char*)a->workspace + nr_align_up((size_t)B * F * sizeof(uint2), 256));
 
     {
         nr_internal::LaunchScope ls("k_face_bbox", stream);
-        k_face_bbox<<<dim3(nchunks, B), kChunk, 0, stream>>>(a->faces, F, S, nchunks, bbox, cbox);
+        k_face_bbox<<<dim3(nchunks, B), kChunk, 0, stream>>>(a->faces, F, S, ngroups, bbox, cbox);
     }
 
     FwdParams p{};
     p.faces = a->faces; p.textures = a->textures; p.bg_batch = a->background_batch;
-    p.bbox = bbox; p.chunk_bbox = cbox;
+    p.bbox = bbox; p.group_bbox = cbox;
     p.fim = a->face_index_map; p.wmap = a->weight_map; p.dmap = a->depth_map; p.rgb = a->rgb_map; p.alpha = a->alpha_map;
     p.out_rgb = a->out_rgb; p.out_alpha = a->out_alpha; p.out_depth = a->out_depth;
-    p.B = B; p.F = F; p.S = S; p.ts = ts; p.nchunks = nchunks;
+    p.B = B; p.F = F; p.S = S; p.ts = ts; p.ngroups = ngroups;
     int tl = kFwdTileLog2Default, threads = kFwdThreadsDefault;  // tuning knobs: NR_B200_FWD_TILE (5|6), NR_B200_FWD_THREADS (128|256)
     if (const char* env = getenv("NR_B200_FWD_TILE")) tl = atoi(env) <= 5 ? 5 : 6;  // 65 = 64 wide x 32 tall
     if (const char* env = getenv("NR_B200_FWD_THREADS")) threads = atoi(env) == 128 ? 128 : 256;
