@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define NR_B200_ABI_VERSION 1
+#define NR_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NR_B200_API __attribute__((visibility("default")))
@@ -60,6 +60,10 @@ extern "C" {
 #define NR_TEX_Z_BATCH0 32u   /* reproduce rasterize.py:389: the texture sampler reads vertex depths of batch  */
                               /* item 0 (reference-exact; clear it for per-item depths)                        */
 #define NR_GRAD_ACCUMULATE 64u /* backward: add into grad_faces / grad_textures instead of zero-filling first */
+#define NR_TEX_FILL_BACK 0x400u /* Renderer.fill_back without materialising the doubled texture tensor            */
+                                /* (renderer.py:78-80): F is even, faces [F/2, F) are the reversed copies of      */
+                                /* [0, F/2); `textures` / `grad_textures` hold F/2 cubes and face f >= F/2 samples */
+                                /* cube f - F/2 with its three texture axes reversed (permute(0,1,4,3,2,5))        */
 
 typedef struct nr_b200_forward_args {
     uint32_t struct_size; /* sizeof(nr_b200_forward_args), for ABI evolution */
@@ -89,6 +93,10 @@ typedef struct nr_b200_forward_args {
     float *out_depth; /* [B,S/2,S/2]   */
     void *workspace; /* nr_b200_forward_workspace_bytes() bytes, 16-byte aligned */
     size_t workspace_bytes;
+    /* ABI 2: per-face RGB light factor of lighting.py:29-52 applied at sample time -- every texel is multiplied by
+     * face_light[b,f,:] before the trilinear blend, bit-identical to sampling the materialised `textures * light`
+     * product (lighting.py:52).  NULL = unlit. */
+    const float *face_light; /* [B,F,3] or NULL */
 } nr_b200_forward_args;
 
 typedef struct nr_b200_backward_args {
@@ -107,9 +115,14 @@ typedef struct nr_b200_backward_args {
     const float *grad_alpha; /* [B,H,W]   */
     const float *grad_depth; /* [B,H,W]   */
     float *grad_faces;    /* [B,F,3,3]                 */
-    float *grad_textures; /* [B,F,ts,ts,ts,3] or NULL  */
+    float *grad_textures; /* [B,F,ts,ts,ts,3] ([B,F/2,...] with NR_TEX_FILL_BACK) or NULL  */
     void *workspace;
     size_t workspace_bytes;
+    /* ABI 2: lighting folded into the sampler.  grad_textures receives the gradient of the UNLIT textures
+     * (weights scaled by face_light); grad_face_light [B,F,3] (may be NULL) receives sum over pixels of
+     * grad_rgb * unlit sample and needs `textures`. */
+    const float *face_light; /* [B,F,3] as given to the forward call, or NULL */
+    float *grad_face_light;  /* [B,F,3] or NULL */
 } nr_b200_backward_args;
 
 /* ABI version of the loaded library (== NR_B200_ABI_VERSION it was built with). */
@@ -134,6 +147,23 @@ NR_B200_API int nr_b200_vertices_to_faces(const float *vertices, const int32_t *
 NR_B200_API int nr_b200_vertices_to_faces_backward(const float *grad_faces, const int32_t *faces, int32_t batch_size,
                                                    int32_t num_vertices, int32_t num_faces, float *grad_vertices,
                                                    uint32_t flags, void *cuda_stream);
+
+/* Camera pipeline of Renderer (reference look_at.py:30-44 / look.py:29-43, then perspective.py:10-18) as one
+ * per-vertex kernel each way:
+ *   d = vertices[b,v,:] - eye[b];   o = rot[b] * d   (rows of rot = camera x, y, z axes; rot NULL = identity,
+ *   eye NULL = origin);   with NR_CAM_PERSPECTIVE:  out = (o.x / o.z / width[b], o.y / o.z / width[b], o.z)
+ * rot [B,9], eye [B,3], width [B] are device arrays; with NR_CAM_SHARED they hold ONE camera used by every item.
+ * The backward writes grad_vertices [B,Nv,3] (may be NULL) and accumulates, per camera, grad_rot [.,9], grad_eye
+ * [.,3], grad_width [.] (each may be NULL; zero-filled first unless NR_GRAD_ACCUMULATE). */
+#define NR_CAM_PERSPECTIVE 0x100u
+#define NR_CAM_SHARED 0x200u
+NR_B200_API int nr_b200_camera_transform(const float *vertices, const float *rot, const float *eye, const float *width,
+                                         int32_t batch_size, int32_t num_vertices, uint32_t flags, float *out,
+                                         void *cuda_stream);
+NR_B200_API int nr_b200_camera_transform_backward(const float *vertices, const float *rot, const float *eye,
+                                                  const float *width, const float *grad_out, int32_t batch_size,
+                                                  int32_t num_vertices, uint32_t flags, float *grad_vertices,
+                                                  float *grad_rot, float *grad_eye, float *grad_width, void *cuda_stream);
 
 /* Number of kernels the last forward/backward call on this thread launched (for launch accounting). */
 NR_B200_API int nr_b200_last_launch_count(void);

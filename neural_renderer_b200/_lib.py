@@ -19,8 +19,11 @@ NR_ANTI_ALIASING = 8
 NR_BG_PER_BATCH = 16
 NR_TEX_Z_BATCH0 = 32
 NR_GRAD_ACCUMULATE = 64
+NR_CAM_PERSPECTIVE = 0x100
+NR_TEX_FILL_BACK = 0x400
+NR_CAM_SHARED = 0x200
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/nr_b200.h declares
 EXPORTED_SYMBOLS = (
@@ -32,6 +35,8 @@ EXPORTED_SYMBOLS = (
     "nr_b200_backward",
     "nr_b200_vertices_to_faces",
     "nr_b200_vertices_to_faces_backward",
+    "nr_b200_camera_transform",
+    "nr_b200_camera_transform_backward",
     "nr_b200_last_launch_count",
     "nr_b200_set_profiling",
     "nr_b200_read_profile",
@@ -50,6 +55,7 @@ class ForwardArgs(ctypes.Structure):
         ("rgb_map", ctypes.c_void_p), ("alpha_map", ctypes.c_void_p),
         ("out_rgb", ctypes.c_void_p), ("out_alpha", ctypes.c_void_p), ("out_depth", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+        ("face_light", ctypes.c_void_p),
     ]
 
 
@@ -65,6 +71,7 @@ class BackwardArgs(ctypes.Structure):
         ("grad_rgb", ctypes.c_void_p), ("grad_alpha", ctypes.c_void_p), ("grad_depth", ctypes.c_void_p),
         ("grad_faces", ctypes.c_void_p), ("grad_textures", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+        ("face_light", ctypes.c_void_p), ("grad_face_light", ctypes.c_void_p),
     ]
 
 
@@ -102,6 +109,12 @@ def load():
     lib.nr_b200_vertices_to_faces_backward.restype = ctypes.c_int
     lib.nr_b200_vertices_to_faces_backward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                                        ctypes.c_int32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+    lib.nr_b200_camera_transform.restype = ctypes.c_int
+    lib.nr_b200_camera_transform.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32,
+                                                                    ctypes.c_void_p, ctypes.c_void_p]
+    lib.nr_b200_camera_transform_backward.restype = ctypes.c_int
+    lib.nr_b200_camera_transform_backward.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32] + \
+        [ctypes.c_void_p] * 5
     lib.nr_b200_last_launch_count.restype = ctypes.c_int
     lib.nr_b200_set_profiling.restype = None
     lib.nr_b200_set_profiling.argtypes = [ctypes.c_int]

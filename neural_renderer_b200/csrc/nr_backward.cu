@@ -52,6 +52,9 @@ struct BwdParams {
     const int* strip_list;  // face indices, grouped by (item, axis, strip)
     float* grad_faces;
     float* grad_textures;
+    const float* textures;
+    const float* face_light;
+    float* grad_face_light;
     int B, F, S, ts, nchunks;
     int W;          // lines per strip (power of two)
     int w_log2, nstrips;
@@ -563,35 +566,82 @@ __global__ void __launch_bounds__(256) k_texture_grad(const __grid_constant__ Bw
     const size_t plane = (size_t)S * S;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel within the image (image orientation)
     const int b = blockIdx.y;
-    if (i >= plane) return;
-    const int fn = __ldg(p.fim + (size_t)b * plane + i);
-    if (fn < 0) return;
-    const int row = (int)(i / S), col = (int)(i % S);
-    const bool aa = (p.flags & NR_ANTI_ALIASING) != 0;
-    const float g0 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 0, row, col);
-    const float g1 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 1, row, col);
-    const float g2 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 2, row, col);
-    const float* wm = p.wmap + (size_t)b * 3 * plane + i;
-    const float w[3] = {__ldg(wm), __ldg(wm + plane), __ldg(wm + 2 * plane)};
-    const float zp = __ldg(p.dmap + (size_t)b * plane + i);
-    const float* v = p.faces + ((size_t)((p.flags & NR_TEX_Z_BATCH0) ? 0 : b) * p.F + fn) * 9;
-    const int ts = p.ts;
-    const nr::TexCoord tc = nr::texture_coords(w, zp, __ldg(v + 2), __ldg(v + 5), __ldg(v + 8), ts, p.tex_cmp, p.tex_val);
-    float* gt = p.grad_textures + ((size_t)b * p.F + fn) * (size_t)(ts * ts * ts) * 3;
-    // The two corners that differ only along texture axis 2 are neighbours in memory: 6 consecutive floats per
-    // corner pair.  They are scattered with the widest vector reductions their alignment allows
-    // (red.global.add.v4/v2.f32, sm_90+): 2-4 requests per pair instead of 6 scalar ones.
-#pragma unroll
-    for (int pr = 0; pr < 4; pr++) {
-        const float w_lo = nr::corner_weight(tc, pr), w_hi = nr::corner_weight(tc, pr | 4);
-        float* t = gt + nr::corner_index(tc, pr, ts) * 3;
-        const float v0 = w_lo * g0, v1 = w_lo * g1, v2 = w_lo * g2, v3 = w_hi * g0, v4 = w_hi * g1, v5 = w_hi * g2;
-        switch ((reinterpret_cast<uintptr_t>(t) >> 2) & 3) {
-            case 0: red_add_v4(t, v0, v1, v2, v3); red_add_v2(t + 4, v4, v5); break;
-            case 2: red_add_v2(t, v0, v1); red_add_v4(t + 2, v2, v3, v4, v5); break;
-            case 3: atomicAdd(t, v0); red_add_v4(t + 1, v1, v2, v3, v4); atomicAdd(t + 5, v5); break;
-            default: atomicAdd(t, v0); red_add_v2(t + 1, v1, v2); red_add_v2(t + 3, v3, v4); atomicAdd(t + 5, v5); break;
+    const int fn = (i < plane) ? __ldg(p.fim + (size_t)b * plane + i) : -1;
+    const bool want_light = p.grad_face_light != nullptr;  // uniform
+    if (fn < 0 && !want_light) return;
+    float gl0 = 0.0f, gl1 = 0.0f, gl2 = 0.0f;  // d loss / d face_light of this pixel
+    if (fn >= 0) {
+        const int row = (int)(i / S), col = (int)(i % S);
+        const bool aa = (p.flags & NR_ANTI_ALIASING) != 0;
+        float g0 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 0, row, col);
+        float g1 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 1, row, col);
+        float g2 = load_grad(p.g_rgb, aa, S, (size_t)b * 3 + 2, row, col);
+        const float* wm = p.wmap + (size_t)b * 3 * plane + i;
+        const float w[3] = {__ldg(wm), __ldg(wm + plane), __ldg(wm + 2 * plane)};
+        const float zp = __ldg(p.dmap + (size_t)b * plane + i);
+        const float* v = p.faces + ((size_t)((p.flags & NR_TEX_Z_BATCH0) ? 0 : b) * p.F + fn) * 9;
+        const int ts = p.ts;
+        const nr::TexCoord tc = nr::texture_coords(w, zp, __ldg(v + 2), __ldg(v + 5), __ldg(v + 8), ts, p.tex_cmp, p.tex_val);
+        // NR_TEX_FILL_BACK: the reversed copy of face f - F/2 shares that face's cube, axes reversed
+        int cube = fn, ncubes = p.F;
+        bool rev = false;
+        if (p.flags & NR_TEX_FILL_BACK) {
+            ncubes = p.F >> 1;
+            if (fn >= ncubes) { cube = fn - ncubes; rev = true; }
         }
+        const size_t cube_off = ((size_t)b * ncubes + cube) * (size_t)(ts * ts * ts) * 3;
+        if (want_light) {  // unlit sample (same blend as the forward pass) times the upstream gradient
+            const float* tex = p.textures + cube_off;
+            float r = 0.0f, g = 0.0f, bl = 0.0f;
+#pragma unroll
+            for (int pn = 0; pn < 8; pn++) {
+                const float cw = nr::corner_weight(tc, pn);
+                const float* t = tex + (rev ? nr::corner_index_rev(tc, pn, ts) : nr::corner_index(tc, pn, ts)) * 3;
+                r = __fmaf_rn(cw, __ldg(t + 0), r);
+                g = __fmaf_rn(cw, __ldg(t + 1), g);
+                bl = __fmaf_rn(cw, __ldg(t + 2), bl);
+            }
+            gl0 = r * g0; gl1 = g * g1; gl2 = bl * g2;
+        }
+        if (p.face_light) {  // d rgb / d texel = weight * light
+            const float* lp = p.face_light + ((size_t)b * p.F + fn) * 3;
+            g0 *= __ldg(lp); g1 *= __ldg(lp + 1); g2 *= __ldg(lp + 2);
+        }
+        float* gt = p.grad_textures + cube_off;
+        // The two corners that differ only along the fastest texture axis (axis 2; axis 0 of a reversed cube) are
+        // neighbours in memory: 6 consecutive floats per corner pair.  They are scattered with the widest vector
+        // reductions their alignment allows (red.global.add.v4/v2.f32, sm_90+): 2-4 requests per pair instead of 6.
+#pragma unroll
+        for (int pr = 0; pr < 4; pr++) {
+            const int pn_lo = rev ? (pr << 1) : pr, pn_hi = rev ? (pn_lo | 1) : (pn_lo | 4);
+            const float w_lo = nr::corner_weight(tc, pn_lo), w_hi = nr::corner_weight(tc, pn_hi);
+            float* t = gt + (rev ? nr::corner_index_rev(tc, pn_lo, ts) : nr::corner_index(tc, pn_lo, ts)) * 3;
+            const float v0 = w_lo * g0, v1 = w_lo * g1, v2 = w_lo * g2, v3 = w_hi * g0, v4 = w_hi * g1, v5 = w_hi * g2;
+            switch ((reinterpret_cast<uintptr_t>(t) >> 2) & 3) {
+                case 0: red_add_v4(t, v0, v1, v2, v3); red_add_v2(t + 4, v4, v5); break;
+                case 2: red_add_v2(t, v0, v1); red_add_v4(t + 2, v2, v3, v4, v5); break;
+                case 3: atomicAdd(t, v0); red_add_v4(t + 1, v1, v2, v3, v4); atomicAdd(t + 5, v5); break;
+                default: atomicAdd(t, v0); red_add_v2(t + 1, v1, v2); red_add_v2(t + 3, v3, v4); atomicAdd(t + 5, v5); break;
+            }
+        }
+    }
+    if (!want_light) return;
+    // warp-aggregated scatter of the light gradient: runs of neighbouring lanes that show the same face
+    const int lane = threadIdx.x & 31;
+    const int fn_prev = __shfl_up_sync(0xffffffffu, fn, 1);
+    const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || fn != fn_prev);
+    const uint32_t later = heads & ~((2u << lane) - 1u);
+    const int run_end = (lane == 31 || later == 0) ? 31 : (__ffs(later) - 2);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const bool take = lane + off <= run_end;
+        const float t0 = __shfl_down_sync(0xffffffffu, gl0, off), t1 = __shfl_down_sync(0xffffffffu, gl1, off),
+                    t2 = __shfl_down_sync(0xffffffffu, gl2, off);
+        if (take) { gl0 += t0; gl1 += t1; gl2 += t2; }
+    }
+    if (fn >= 0 && ((heads >> lane) & 1u)) {
+        float* gl = p.grad_face_light + ((size_t)b * p.F + fn) * 3;
+        atomicAdd(gl, gl0); atomicAdd(gl + 1, gl1); atomicAdd(gl + 2, gl2);
     }
 }
 
@@ -726,6 +776,8 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
     if (!a->faces || !a->face_index_map || !a->weight_map || !a->depth_map || !a->grad_faces) return NR_ERR_INVALID_ARG;
     const bool rgb = (flags & NR_RETURN_RGB) != 0, alpha = (flags & NR_RETURN_ALPHA) != 0, depth = (flags & NR_RETURN_DEPTH) != 0;
     if (rgb && (!a->rgb_map || !a->grad_textures || ts < 2)) return NR_ERR_INVALID_ARG;
+    if (rgb && (flags & NR_TEX_FILL_BACK) && (F & 1)) return NR_ERR_INVALID_ARG;
+    if (rgb && a->grad_face_light && !a->textures) return NR_ERR_INVALID_ARG;
     if ((flags & NR_ANTI_ALIASING) && (S & 1)) return NR_ERR_INVALID_ARG;
     if (S > 32767 || B > 65535) return NR_ERR_UNSUPPORTED;
     if ((size_t)B * F * 2 * kWideStrips >= (size_t)0x7FFFFFFF) return NR_ERR_UNSUPPORTED;  // 32-bit list offsets
@@ -736,7 +788,10 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
     if (!(flags & NR_GRAD_ACCUMULATE)) {
         nr_internal::prof_begin("memset_grads", stream);
         if (cudaMemsetAsync(a->grad_faces, 0, (size_t)B * F * 9 * sizeof(float), stream) != cudaSuccess) return NR_ERR_CUDA;
-        if (rgb && cudaMemsetAsync(a->grad_textures, 0, (size_t)B * F * ts * ts * ts * 3 * sizeof(float), stream) != cudaSuccess)
+        const size_t ncubes = (flags & NR_TEX_FILL_BACK) ? (size_t)F / 2 : (size_t)F;
+        if (rgb && cudaMemsetAsync(a->grad_textures, 0, (size_t)B * ncubes * ts * ts * ts * 3 * sizeof(float), stream) != cudaSuccess)
+            return NR_ERR_CUDA;
+        if (rgb && a->grad_face_light && cudaMemsetAsync(a->grad_face_light, 0, (size_t)B * F * 3 * sizeof(float), stream) != cudaSuccess)
             return NR_ERR_CUDA;
         nr_internal::prof_end(stream);
     }
@@ -745,6 +800,7 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
     p.faces = a->faces; p.fim = a->face_index_map; p.wmap = a->weight_map; p.dmap = a->depth_map; p.rgb = a->rgb_map;
     p.g_rgb = rgb ? a->grad_rgb : nullptr; p.g_alpha = alpha ? a->grad_alpha : nullptr; p.g_depth = depth ? a->grad_depth : nullptr;
     p.grad_faces = a->grad_faces; p.grad_textures = a->grad_textures;
+    p.textures = a->textures; p.face_light = rgb ? a->face_light : nullptr; p.grad_face_light = rgb ? a->grad_face_light : nullptr;
     p.B = B; p.F = F; p.S = S; p.ts = ts;
     p.flags = flags;
     p.eps = (float)a->eps;

@@ -52,6 +52,7 @@ struct FwdParams {
     const float* faces;
     const float* textures;
     const float* bg_batch;
+    const float* face_light;
     const uint2* bbox;
     const uint2* group_bbox;
     int32_t* fim;
@@ -137,15 +138,32 @@ __device__ __forceinline__ Shaded shade_pixel(const FwdParams& p, const float (*
         }
         const int ts = p.ts;
         const nr::TexCoord tc = nr::texture_coords(w, zp, z0, z1, z2, ts, p.tex_cmp, p.tex_val);
-        const float* tex = p.textures + ((size_t)b * p.F + fn) * (size_t)(ts * ts * ts) * 3;
+        // NR_TEX_FILL_BACK: the reversed copy of face f - F/2 samples that face's cube with reversed axes
+        int cube = fn, ncubes = p.F;
+        bool rev = false;
+        if (p.flags & NR_TEX_FILL_BACK) {
+            ncubes = p.F >> 1;
+            if (fn >= ncubes) { cube = fn - ncubes; rev = true; }
+        }
+        const float* tex = p.textures + ((size_t)b * ncubes + cube) * (size_t)(ts * ts * ts) * 3;
+        float l0 = 1.0f, l1 = 1.0f, l2 = 1.0f;
+        const bool lit = p.face_light != nullptr;
+        if (lit) {
+            const float* lp = p.face_light + ((size_t)b * p.F + fn) * 3;
+            l0 = __ldg(lp); l1 = __ldg(lp + 1); l2 = __ldg(lp + 2);
+        }
         float r = 0.0f, g = 0.0f, bl = 0.0f;
 #pragma unroll
         for (int pn = 0; pn < 8; pn++) {
             const float cw = nr::corner_weight(tc, pn);
-            const float* t = tex + nr::corner_index(tc, pn, ts) * 3;
-            r = __fmaf_rn(cw, __ldg(t + 0), r);
-            g = __fmaf_rn(cw, __ldg(t + 1), g);
-            bl = __fmaf_rn(cw, __ldg(t + 2), bl);
+            const float* t = tex + (rev ? nr::corner_index_rev(tc, pn, ts) : nr::corner_index(tc, pn, ts)) * 3;
+            float t0 = __ldg(t + 0), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
+            if (lit) {  // lighting.py:52 texel * light, rounded like the materialised product
+                t0 = __fmul_rn(t0, l0); t1 = __fmul_rn(t1, l1); t2 = __fmul_rn(t2, l2);
+            }
+            r = __fmaf_rn(cw, t0, r);
+            g = __fmaf_rn(cw, t1, g);
+            bl = __fmaf_rn(cw, t2, bl);
         }
         o.r = r; o.g = g; o.b = bl;
     }
@@ -461,6 +479,7 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
     if (!a->faces || !a->face_index_map || !a->weight_map || !a->depth_map) return NR_ERR_INVALID_ARG;
     if (flags & NR_RETURN_RGB) {
         if (!a->textures || !a->rgb_map || ts < 2) return NR_ERR_INVALID_ARG;
+        if ((flags & NR_TEX_FILL_BACK) && (F & 1)) return NR_ERR_INVALID_ARG;
         if ((flags & NR_BG_PER_BATCH) && !a->background_batch) return NR_ERR_INVALID_ARG;
     }
     if ((flags & NR_ANTI_ALIASING) && (S & 1)) return NR_ERR_INVALID_ARG;
@@ -481,6 +500,7 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
 
     FwdParams p{};
     p.faces = a->faces; p.textures = a->textures; p.bg_batch = a->background_batch;
+    p.face_light = (flags & NR_RETURN_RGB) ? a->face_light : nullptr;
     p.bbox = bbox; p.group_bbox = cbox;
     p.fim = a->face_index_map; p.wmap = a->weight_map; p.dmap = a->depth_map; p.rgb = a->rgb_map; p.alpha = a->alpha_map;
     p.out_rgb = a->out_rgb; p.out_alpha = a->out_alpha; p.out_depth = a->out_depth;

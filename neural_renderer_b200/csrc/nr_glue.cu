@@ -4,6 +4,11 @@
 // The reference forms d loss / d vertex through Chainer's generic get_item backward (a scatter-add of the
 // [B,F,3,3] face gradients into [B*Nv,3]); here it is one pass of fp32 vector reductions into the vertex gradient,
 // reading grad_faces exactly once.
+//
+// Camera pipeline: look_at / look (look_at.py:30-44, look.py:29-43: subtract the
+// eye, rotate into the camera frame) and perspective (perspective.py:10-18: x / z / tan(angle)) as ONE per-vertex
+// kernel each way; the backward also reduces the gradients of the 3x3 rotation, the eye and the width per batch
+// item, so camera-pose optimisation (examples/example4.py) differentiates through it.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -41,6 +46,108 @@ __global__ void __launch_bounds__(256) k_v2f_scatter(const float* __restrict__ g
     atomicAdd(v, gx); atomicAdd(v + 1, gy); atomicAdd(v + 2, gz);
 }
 
+
+struct CamItem {
+    float r[9], e[3], w;
+};
+__device__ __forceinline__ CamItem load_cam(const float* rot, const float* eye, const float* width, int item) {
+    CamItem c;
+#pragma unroll
+    for (int k = 0; k < 9; k++) c.r[k] = rot ? __ldg(rot + (size_t)item * 9 + k) : ((k % 4 == 0) ? 1.0f : 0.0f);
+#pragma unroll
+    for (int k = 0; k < 3; k++) c.e[k] = eye ? __ldg(eye + (size_t)item * 3 + k) : 0.0f;
+    c.w = width ? __ldg(width + item) : 1.0f;
+    return c;
+}
+
+// out = perspective(rot * (v - eye)): one thread per vertex
+__global__ void __launch_bounds__(256) k_camera_fwd(const float* __restrict__ vertices, const float* __restrict__ rot,
+                                                    const float* __restrict__ eye, const float* __restrict__ width,
+                                                    int Nv, uint32_t flags, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Nv) return;
+    const CamItem c = load_cam(rot, eye, width, (flags & NR_CAM_SHARED) ? 0 : b);
+    const float* v = vertices + ((size_t)b * Nv + i) * 3;
+    const float d0 = __ldg(v) - c.e[0], d1 = __ldg(v + 1) - c.e[1], d2 = __ldg(v + 2) - c.e[2];
+    float ox = fmaf(d2, c.r[2], fmaf(d1, c.r[1], d0 * c.r[0]));
+    float oy = fmaf(d2, c.r[5], fmaf(d1, c.r[4], d0 * c.r[3]));
+    const float oz = fmaf(d2, c.r[8], fmaf(d1, c.r[7], d0 * c.r[6]));
+    if (flags & NR_CAM_PERSPECTIVE) {  // perspective.py:15-17: x / z / width
+        ox = ox / oz / c.w;
+        oy = oy / oz / c.w;
+    }
+    float* o = out + ((size_t)b * Nv + i) * 3;
+    o[0] = ox; o[1] = oy; o[2] = oz;
+}
+
+// grad_vertices = rot^T * g_o with g_o the gradient in front of the perspective division; per-item reductions
+// grad_rot[j][k] = sum_v g_o[j] * d[k], grad_eye = -sum_v grad_vertex, grad_width = -sum_v (gx*x + gy*y) / width
+__global__ void __launch_bounds__(256) k_camera_bwd(const float* __restrict__ vertices, const float* __restrict__ rot,
+                                                    const float* __restrict__ eye, const float* __restrict__ width,
+                                                    const float* __restrict__ grad_out, int Nv, uint32_t flags,
+                                                    float* __restrict__ grad_vertices, float* __restrict__ grad_rot,
+                                                    float* __restrict__ grad_eye, float* __restrict__ grad_width) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int item = (flags & NR_CAM_SHARED) ? 0 : b;
+    const CamItem c = load_cam(rot, eye, width, item);
+    float acc[13];
+#pragma unroll
+    for (int k = 0; k < 13; k++) acc[k] = 0.0f;
+    if (i < Nv) {
+        const float* v = vertices + ((size_t)b * Nv + i) * 3;
+        const float* g = grad_out + ((size_t)b * Nv + i) * 3;
+        const float d[3] = {__ldg(v) - c.e[0], __ldg(v + 1) - c.e[1], __ldg(v + 2) - c.e[2]};
+        float go[3] = {__ldg(g), __ldg(g + 1), __ldg(g + 2)};
+        if (flags & NR_CAM_PERSPECTIVE) {
+            const float ox = fmaf(d[2], c.r[2], fmaf(d[1], c.r[1], d[0] * c.r[0]));
+            const float oy = fmaf(d[2], c.r[5], fmaf(d[1], c.r[4], d[0] * c.r[3]));
+            const float oz = fmaf(d[2], c.r[8], fmaf(d[1], c.r[7], d[0] * c.r[6]));
+            const float x = ox / oz / c.w, y = oy / oz / c.w;
+            const float s = go[0] * x + go[1] * y;
+            acc[12] = -s / c.w;
+            go[2] = go[2] - s / oz;
+            go[0] = go[0] / oz / c.w;
+            go[1] = go[1] / oz / c.w;
+        }
+        float gv[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) gv[k] = fmaf(go[2], c.r[6 + k], fmaf(go[1], c.r[3 + k], go[0] * c.r[k]));
+        if (grad_vertices) {
+            float* o = grad_vertices + ((size_t)b * Nv + i) * 3;
+            o[0] = gv[0]; o[1] = gv[1]; o[2] = gv[2];
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) acc[3 * j + k] = go[j] * d[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) acc[9 + k] = -gv[k];
+    }
+    if (!(grad_rot || grad_eye || grad_width)) return;  // uniform
+    // block reduction of the 13 camera terms, then one atomic per term and CTA
+    __shared__ float red[8][13];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 13; k++) {
+        float t = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) red[warp][k] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 13) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += red[w][threadIdx.x];
+        const int k = threadIdx.x;
+        if (k < 9) { if (grad_rot) atomicAdd(grad_rot + (size_t)item * 9 + k, t); }
+        else if (k < 12) { if (grad_eye) atomicAdd(grad_eye + (size_t)item * 3 + (k - 9), t); }
+        else if (grad_width && (flags & NR_CAM_PERSPECTIVE)) atomicAdd(grad_width + item, t);
+    }
+}
+
 }  // namespace
 
 extern "C" int nr_b200_vertices_to_faces(const float* vertices, const int32_t* faces, int32_t B, int32_t Nv, int32_t Nf,
@@ -68,6 +175,41 @@ extern "C" int nr_b200_vertices_to_faces_backward(const float* grad_faces, const
     {
         nr_internal::LaunchScope ls("k_v2f_scatter", stream);
         k_v2f_scatter<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, stream>>>(grad_faces, faces, Nv, n, grad_vertices);
+    }
+    return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
+}
+
+extern "C" int nr_b200_camera_transform(const float* vertices, const float* rot, const float* eye, const float* width,
+                                        int32_t B, int32_t Nv, uint32_t flags, float* out, void* cuda_stream) {
+    nr_internal::launch_count() = 0;
+    if (!vertices || !out || B <= 0 || Nv <= 0 || B > 65535) return NR_ERR_INVALID_ARG;
+    if ((flags & NR_CAM_PERSPECTIVE) && !width) return NR_ERR_INVALID_ARG;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    {
+        nr_internal::LaunchScope ls("k_camera_fwd", stream);
+        k_camera_fwd<<<dim3((unsigned)((Nv + 255) / 256), B), 256, 0, stream>>>(vertices, rot, eye, width, Nv, flags, out);
+    }
+    return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
+}
+
+extern "C" int nr_b200_camera_transform_backward(const float* vertices, const float* rot, const float* eye,
+                                                 const float* width, const float* grad_out, int32_t B, int32_t Nv,
+                                                 uint32_t flags, float* grad_vertices, float* grad_rot, float* grad_eye,
+                                                 float* grad_width, void* cuda_stream) {
+    nr_internal::launch_count() = 0;
+    if (!vertices || !grad_out || B <= 0 || Nv <= 0 || B > 65535) return NR_ERR_INVALID_ARG;
+    if ((flags & NR_CAM_PERSPECTIVE) && !width) return NR_ERR_INVALID_ARG;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const size_t items = (flags & NR_CAM_SHARED) ? 1 : (size_t)B;
+    if (!(flags & NR_GRAD_ACCUMULATE)) {  // the camera terms are accumulated with atomics
+        if (grad_rot && cudaMemsetAsync(grad_rot, 0, items * 9 * sizeof(float), stream) != cudaSuccess) return NR_ERR_CUDA;
+        if (grad_eye && cudaMemsetAsync(grad_eye, 0, items * 3 * sizeof(float), stream) != cudaSuccess) return NR_ERR_CUDA;
+        if (grad_width && cudaMemsetAsync(grad_width, 0, items * sizeof(float), stream) != cudaSuccess) return NR_ERR_CUDA;
+    }
+    {
+        nr_internal::LaunchScope ls("k_camera_bwd", stream);
+        k_camera_bwd<<<dim3((unsigned)((Nv + 255) / 256), B), 256, 0, stream>>>(vertices, rot, eye, width, grad_out, Nv, flags,
+                                                                               grad_vertices, grad_rot, grad_eye, grad_width);
     }
     return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
 }

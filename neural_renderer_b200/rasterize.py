@@ -52,7 +52,7 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def _check_inputs(faces, textures, return_rgb):
+def _check_inputs(faces, textures, return_rgb, face_light=None, textures_fill_back=False):
     # rasterize.py:66-90 (chainer type_check) -> TypeError / ValueError with the same conditions
     if not isinstance(faces, torch.Tensor):
         raise TypeError("faces must be a torch.Tensor")
@@ -65,11 +65,19 @@ def _check_inputs(faces, textures, return_rgb):
             raise TypeError("textures are required to draw RGB")
         if not textures.is_floating_point():
             raise TypeError("textures must be floating point")
+        num_cubes = faces.shape[1] // 2 if textures_fill_back else faces.shape[1]
+        if textures_fill_back and faces.shape[1] % 2:
+            raise ValueError("textures_fill_back needs an even number of faces (front faces, then their reversed copies)")
         if (textures.dim() != 6 or textures.shape[2] < 2 or textures.shape[2] != textures.shape[3]
                 or textures.shape[3] != textures.shape[4] or textures.shape[5] != 3
-                or textures.shape[0] != faces.shape[0] or textures.shape[1] != faces.shape[1]):
+                or textures.shape[0] != faces.shape[0] or textures.shape[1] != num_cubes):
             raise ValueError("textures must have shape [batch size, num faces, ts, ts, ts, 3] with ts >= 2 and match "
                              "faces, got %s" % (tuple(textures.shape),))
+    if return_rgb and face_light is not None:
+        if not isinstance(face_light, torch.Tensor) or tuple(face_light.shape) != (faces.shape[0], faces.shape[1], 3):
+            raise ValueError("face_light must have shape [batch size, num faces, 3]")
+        if not face_light.is_cuda:
+            raise NotImplementedError("neural_renderer_b200 has no CPU implementation (inputs must be CUDA tensors)")
     if not faces.is_cuda or (return_rgb and not textures.is_cuda):
         raise NotImplementedError("neural_renderer_b200 has no CPU implementation (inputs must be CUDA tensors)")
 
@@ -128,11 +136,12 @@ class _RasterizeFunction(torch.autograd.Function):
     maps (returned non-differentiable so tests / the `Rasterize` object can look at them)."""
 
     @staticmethod
-    def forward(ctx, faces, textures, cfg):
+    def forward(ctx, faces, textures, face_light, cfg):
         lib = _lib.load()
         dev = faces.device
         faces_c = faces.detach().contiguous()
         tex_c = textures.detach().contiguous() if textures is not None else None
+        light_c = face_light.detach().to(torch.float32).contiguous() if face_light is not None else None
         B, F = faces_c.shape[:2]
         S = cfg.S
         ts = int(tex_c.shape[2]) if tex_c is not None else 0
@@ -167,11 +176,14 @@ class _RasterizeFunction(torch.autograd.Function):
             a.rgb_map, a.alpha_map = _ptr(rgb_map), _ptr(alpha_map)
             a.out_rgb, a.out_alpha, a.out_depth = _ptr(out_rgb), _ptr(out_alpha), _ptr(out_depth)
             a.workspace, a.workspace_bytes = _ptr(ws), ws_bytes
+            a.face_light = _ptr(light_c)
             _lib.check(lib.nr_b200_forward(ctypes.byref(a), _stream_ptr(dev)))
         ctx.cfg = cfg
         ctx.ts = ts
         ctx.tex_shape = tuple(textures.shape) if textures is not None else None
-        ctx.save_for_backward(faces_c, fim, wmap, dmap, rgb_map)
+        # the unlit textures are only needed again for d loss / d face_light
+        need_light_grad = light_c is not None and ctx.needs_input_grad[2]
+        ctx.save_for_backward(faces_c, fim, wmap, dmap, rgb_map, light_c, tex_c if need_light_grad else None)
         if cfg.aa:
             rgb_o, alpha_o, depth_o = out_rgb, out_alpha, out_depth
         else:
@@ -183,7 +195,7 @@ class _RasterizeFunction(torch.autograd.Function):
     def backward(ctx, g_rgb, g_alpha, g_depth, _g_fim, _g_wmap):
         lib = _lib.load()
         cfg = ctx.cfg
-        faces_c, fim, wmap, dmap, rgb_map = ctx.saved_tensors
+        faces_c, fim, wmap, dmap, rgb_map, light_c, tex_c = ctx.saved_tensors
         dev = faces_c.device
         B, F = faces_c.shape[:2]
         want_rgb = bool(cfg.flags & _lib.NR_RETURN_RGB)
@@ -199,6 +211,7 @@ class _RasterizeFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             grad_faces = torch.empty_like(faces_c)
             grad_textures = torch.empty(ctx.tex_shape, dtype=torch.float32, device=dev) if want_rgb else None
+            grad_light = torch.empty_like(light_c) if (want_rgb and tex_c is not None) else None
             ws_bytes = lib.nr_b200_backward_workspace_bytes(B, F, cfg.S, ctx.ts, cfg.flags)
             ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
             a = _lib.BackwardArgs()
@@ -206,25 +219,28 @@ class _RasterizeFunction(torch.autograd.Function):
             a.flags = cfg.flags
             a.batch_size, a.num_faces, a.raster_size, a.texture_size = B, F, cfg.S, ctx.ts
             a.eps = cfg.eps
-            a.faces, a.textures = _ptr(faces_c), None
+            a.faces, a.textures = _ptr(faces_c), _ptr(tex_c)
+            a.face_light, a.grad_face_light = _ptr(light_c), _ptr(grad_light)
             a.face_index_map, a.weight_map, a.depth_map, a.rgb_map = _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(rgb_map)
             a.grad_rgb, a.grad_alpha, a.grad_depth = _ptr(g_rgb), _ptr(g_alpha), _ptr(g_depth)
             a.grad_faces, a.grad_textures = _ptr(grad_faces), _ptr(grad_textures)
             a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
             _lib.check(lib.nr_b200_backward(ctypes.byref(a), _stream_ptr(dev)))
-        return grad_faces, grad_textures, None
+        return grad_faces, grad_textures, grad_light, None
 
 
 def _run(faces, textures, image_size, anti_aliasing, near, far, eps, background_color, return_rgb, return_alpha,
-         return_depth):
-    _check_inputs(faces, textures, return_rgb)
+         return_depth, face_light=None, textures_fill_back=False):
+    _check_inputs(faces, textures, return_rgb, face_light, textures_fill_back)
     if faces.dtype != torch.float32:
         faces = faces.float()
     if return_rgb and textures.dtype != torch.float32:
         textures = textures.float()
     cfg = _make_config(image_size, anti_aliasing, near, far, eps, background_color, return_rgb, return_alpha,
                        return_depth, faces.device, faces.shape[0])
-    return _RasterizeFunction.apply(faces, textures if return_rgb else None, cfg)
+    if return_rgb and textures_fill_back:
+        cfg.flags |= _lib.NR_TEX_FILL_BACK
+    return _RasterizeFunction.apply(faces, textures if return_rgb else None, face_light if return_rgb else None, cfg)
 
 
 def rasterize_rgbad(
@@ -239,12 +255,21 @@ def rasterize_rgbad(
         return_rgb=True,
         return_alpha=True,
         return_depth=True,
+        *,
+        face_light=None,
+        textures_fill_back=False,
 ):
     """Generate RGB, alpha channel, and depth images from faces and textures (for RGB).  rasterize.py:900-977.
 
-    Returns {'rgb': [B,3,H,W], 'alpha': [B,H,W], 'depth': [B,H,W]} (None for the ones not requested)."""
+    Returns {'rgb': [B,3,H,W], 'alpha': [B,H,W], 'depth': [B,H,W]} (None for the ones not requested).
+
+    Keyword-only extensions (not in the reference; `Renderer.render` uses them so that neither the lit nor the
+    fill_back-doubled texture tensor is ever materialised):
+      face_light [B,F,3]      per-face RGB factor of `lighting` applied at sample time (== sampling textures * light)
+      textures_fill_back      faces [F/2, F) are the reversed copies of [0, F/2) and `textures` holds only the F/2
+                              original cubes (the copies read them with reversed axes, renderer.py:80)"""
     rgb, alpha, depth, _, _ = _run(faces, textures, image_size, anti_aliasing, near, far, eps, background_color,
-                                   return_rgb, return_alpha, return_depth)
+                                   return_rgb, return_alpha, return_depth, face_light, textures_fill_back)
     return {
         'rgb': rgb if return_rgb else None,
         'alpha': alpha if return_alpha else None,
@@ -261,10 +286,14 @@ def rasterize(
         far=DEFAULT_FAR,
         eps=DEFAULT_EPS,
         background_color=DEFAULT_BACKGROUND_COLOR,
+        *,
+        face_light=None,
+        textures_fill_back=False,
 ):
-    """RGB images [B,3,H,W] from faces and textures.  rasterize.py:980-1008."""
+    """RGB images [B,3,H,W] from faces and textures.  rasterize.py:980-1008 (keyword-only extras: rasterize_rgbad)."""
     return rasterize_rgbad(
-        faces, textures, image_size, anti_aliasing, near, far, eps, background_color, True, False, False)['rgb']
+        faces, textures, image_size, anti_aliasing, near, far, eps, background_color, True, False, False,
+        face_light=face_light, textures_fill_back=textures_fill_back)['rgb']
 
 
 def rasterize_silhouettes(

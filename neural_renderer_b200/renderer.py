@@ -36,14 +36,13 @@ class Renderer(object):
         # rasterization
         self.rasterizer_eps = 1e-3
 
+        # not in the reference: fold lighting / fill_back texture handling into the rasterizer (same pixels)
+        self.fused = True
+
     def _transform(self, vertices):
-        if self.camera_mode == 'look_at':
-            vertices = F.look_at(vertices, self.eye)
-        elif self.camera_mode == 'look':
-            vertices = F.look(vertices, self.eye, self.camera_direction)
-        if self.perspective:
-            vertices = F.perspective(vertices, angle=self.viewing_angle)
-        return vertices
+        # renderer.py:41-50 (look_at / look, then perspective), fused into one kernel on CUDA
+        return F.camera_transform(vertices, self.eye, self.camera_mode, self.camera_direction, self.perspective,
+                                  self.viewing_angle)
 
     def render_silhouettes(self, vertices, faces):
         if self.fill_back:
@@ -61,18 +60,25 @@ class Renderer(object):
         return rasterize_depth(faces, self.image_size, self.anti_aliasing)  # renderer.py:72
 
     def render(self, vertices, faces, textures):
+        fused = (self.fused and vertices.is_cuda and textures.is_cuda and vertices.dtype == torch.float32
+                 and textures.dtype == torch.float32)
         if self.fill_back:
             faces = torch.cat((faces, faces.flip(2)), dim=1)
-            textures = torch.cat((textures, textures.permute(0, 1, 4, 3, 2, 5)), dim=1)
+            if not fused:
+                textures = torch.cat((textures, textures.permute(0, 1, 4, 3, 2, 5)), dim=1)
         faces_lighting = F.vertices_to_faces(vertices, faces)
-        textures = F.lighting(
-            faces_lighting,
-            textures,
-            self.light_intensity_ambient,
-            self.light_intensity_directional,
-            self.light_color_ambient,
-            self.light_color_directional,
-            self.light_direction)
+        light_args = (self.light_intensity_ambient, self.light_intensity_directional, self.light_color_ambient,
+                      self.light_color_directional, self.light_direction)
+        if fused:
+            # lighting.py:29-52 and renderer.py:78-80 folded into the sampler: neither `textures * light` nor the
+            # doubled texture tensor exists; pixel values are bit-identical to the op-by-op formulation
+            light = F.face_light(faces_lighting, *light_args)
+            vertices = self._transform(vertices)
+            faces = F.vertices_to_faces(vertices, faces)
+            return rasterize(
+                faces, textures, self.image_size, self.anti_aliasing, self.near, self.far, self.rasterizer_eps,
+                self.background_color, face_light=light, textures_fill_back=self.fill_back)
+        textures = F.lighting(faces_lighting, textures, *light_args)
         vertices = self._transform(vertices)
         faces = F.vertices_to_faces(vertices, faces)
         return rasterize(
