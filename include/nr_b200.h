@@ -165,6 +165,20 @@ NR_B200_API int nr_b200_camera_transform_backward(const float *vertices, const f
                                                   int32_t num_vertices, uint32_t flags, float *grad_vertices,
                                                   float *grad_rot, float *grad_eye, float *grad_width, void *cuda_stream);
 
+/* Per-face light factor of lighting.py:29-51, straight from vertices and face indices:
+ *   n = normalize(cross(v0 - v1, v2 - v1))  (x / (|x| + 1e-5), like chainer.functions.normalize)
+ *   face_light[b,f,:] = ambient + directional * max(n . direction, 0)
+ * light_params [B,9] (or [1,9] with NR_CAM_SHARED) = {intensity_ambient * color_ambient (3),
+ * intensity_directional * color_directional (3), direction (3)}, device memory.  The factor is consumed by
+ * nr_b200_forward_args.face_light; the backward turns d loss / d face_light (nr_b200_backward_args.grad_face_light)
+ * into d loss / d vertices (zero-filled first unless NR_GRAD_ACCUMULATE). */
+NR_B200_API int nr_b200_face_lighting(const float *vertices, const int32_t *faces, const float *light_params,
+                                      int32_t batch_size, int32_t num_vertices, int32_t num_faces, uint32_t flags,
+                                      float *face_light, void *cuda_stream);
+NR_B200_API int nr_b200_face_lighting_backward(const float *vertices, const int32_t *faces, const float *light_params,
+                                               const float *grad_face_light, int32_t batch_size, int32_t num_vertices,
+                                               int32_t num_faces, uint32_t flags, float *grad_vertices, void *cuda_stream);
+
 /* Number of kernels the last forward/backward call on this thread launched (for launch accounting). */
 NR_B200_API int nr_b200_last_launch_count(void);
 

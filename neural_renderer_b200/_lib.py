@@ -37,6 +37,8 @@ EXPORTED_SYMBOLS = (
     "nr_b200_vertices_to_faces_backward",
     "nr_b200_camera_transform",
     "nr_b200_camera_transform_backward",
+    "nr_b200_face_lighting",
+    "nr_b200_face_lighting_backward",
     "nr_b200_last_launch_count",
     "nr_b200_set_profiling",
     "nr_b200_read_profile",
@@ -115,6 +117,12 @@ def load():
     lib.nr_b200_camera_transform_backward.restype = ctypes.c_int
     lib.nr_b200_camera_transform_backward.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32] + \
         [ctypes.c_void_p] * 5
+    lib.nr_b200_face_lighting.restype = ctypes.c_int
+    lib.nr_b200_face_lighting.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int32] * 3 + [ctypes.c_uint32, ctypes.c_void_p,
+                                                                                       ctypes.c_void_p]
+    lib.nr_b200_face_lighting_backward.restype = ctypes.c_int
+    lib.nr_b200_face_lighting_backward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int32] * 3 + [ctypes.c_uint32, ctypes.c_void_p,
+                                                                                                ctypes.c_void_p]
     lib.nr_b200_last_launch_count.restype = ctypes.c_int
     lib.nr_b200_set_profiling.restype = None
     lib.nr_b200_set_profiling.argtypes = [ctypes.c_int]

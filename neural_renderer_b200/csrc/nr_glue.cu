@@ -9,6 +9,10 @@
 // eye, rotate into the camera frame) and perspective (perspective.py:10-18: x / z / tan(angle)) as ONE per-vertex
 // kernel each way; the backward also reduces the gradients of the 3x3 rotation, the eye and the width per batch
 // item, so camera-pose optimisation (examples/example4.py) differentiates through it.
+//
+// Lighting: the per-face RGB factor of lighting.py:29-51 straight from vertices and
+// face indices (no gathered [B,F,3,3] tensor), and its backward as a scatter-add into the vertex gradient.  The
+// factor itself is applied inside the rasterizer's sampler (nr_b200_forward_args.face_light).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -148,6 +152,98 @@ __global__ void __launch_bounds__(256) k_camera_bwd(const float* __restrict__ ve
     }
 }
 
+
+// light parameters of one item: {ambient rgb (intensity * colour), directional rgb (intensity * colour), direction}
+struct LightItem {
+    float amb[3], dir_rgb[3], dir[3];
+};
+__device__ __forceinline__ LightItem load_light(const float* params, int item) {
+    LightItem L;
+    const float* q = params + (size_t)item * 9;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { L.amb[k] = __ldg(q + k); L.dir_rgb[k] = __ldg(q + 3 + k); L.dir[k] = __ldg(q + 6 + k); }
+    return L;
+}
+struct FaceGeom {
+    float a[3], b[3], c[3], len;  // a = v0 - v1, b = v2 - v1, c = a x b (lighting.py:40-43)
+    int i0, i1, i2;
+    bool ok;
+};
+__device__ __forceinline__ FaceGeom face_geom(const float* vertices, const int32_t* faces, int b, int Nv, int Nf, int f) {
+    FaceGeom G;
+    const int32_t* fi = faces + ((size_t)b * Nf + f) * 3;
+    G.i0 = __ldg(fi); G.i1 = __ldg(fi + 1); G.i2 = __ldg(fi + 2);
+    G.ok = (unsigned)G.i0 < (unsigned)Nv && (unsigned)G.i1 < (unsigned)Nv && (unsigned)G.i2 < (unsigned)Nv;
+    float v[3][3] = {};
+    if (G.ok) {
+        const int idx[3] = {G.i0, G.i1, G.i2};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float* p = vertices + ((size_t)b * Nv + idx[k]) * 3;
+            v[k][0] = __ldg(p); v[k][1] = __ldg(p + 1); v[k][2] = __ldg(p + 2);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { G.a[k] = v[0][k] - v[1][k]; G.b[k] = v[2][k] - v[1][k]; }
+    G.c[0] = G.a[1] * G.b[2] - G.a[2] * G.b[1];
+    G.c[1] = G.a[2] * G.b[0] - G.a[0] * G.b[2];
+    G.c[2] = G.a[0] * G.b[1] - G.a[1] * G.b[0];
+    G.len = sqrtf((G.c[0] * G.c[0] + G.c[1] * G.c[1]) + G.c[2] * G.c[2]);
+    return G;
+}
+
+// light[b,f,:] = ambient + directional * relu(normal . direction), normal = c / (|c| + 1e-5)
+__global__ void __launch_bounds__(256) k_face_light_fwd(const float* __restrict__ vertices, const int32_t* __restrict__ faces,
+                                                        const float* __restrict__ params, int Nv, int Nf, uint32_t flags,
+                                                        float* __restrict__ light) {
+    const int b = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= Nf) return;
+    const LightItem L = load_light(params, (flags & NR_CAM_SHARED) ? 0 : b);
+    const FaceGeom G = face_geom(vertices, faces, b, Nv, Nf, f);
+    const float inv = 1.0f / (G.len + 1e-5f);
+    const float cosv = fmaxf((G.c[0] * inv * L.dir[0] + G.c[1] * inv * L.dir[1]) + G.c[2] * inv * L.dir[2], 0.0f);
+    float* o = light + ((size_t)b * Nf + f) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[k] = L.amb[k] + L.dir_rgb[k] * cosv;
+}
+
+// d loss / d vertices from d loss / d light: through relu, the normalisation and the cross product
+__global__ void __launch_bounds__(256) k_face_light_bwd(const float* __restrict__ vertices, const int32_t* __restrict__ faces,
+                                                        const float* __restrict__ params, const float* __restrict__ grad_light,
+                                                        int Nv, int Nf, uint32_t flags, float* __restrict__ grad_vertices) {
+    const int b = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= Nf) return;
+    const LightItem L = load_light(params, (flags & NR_CAM_SHARED) ? 0 : b);
+    const FaceGeom G = face_geom(vertices, faces, b, Nv, Nf, f);
+    if (!G.ok) return;
+    const float inv = 1.0f / (G.len + 1e-5f);
+    const float n[3] = {G.c[0] * inv, G.c[1] * inv, G.c[2] * inv};
+    const float dot = (n[0] * L.dir[0] + n[1] * L.dir[1]) + n[2] * L.dir[2];
+    if (!(dot > 0.0f)) return;  // relu
+    const float* g = grad_light + ((size_t)b * Nf + f) * 3;
+    const float gcos = (__ldg(g) * L.dir_rgb[0] + __ldg(g + 1) * L.dir_rgb[1]) + __ldg(g + 2) * L.dir_rgb[2];
+    if (gcos == 0.0f) return;
+    // n = c / (len + eps):  g_c = g_n / (len + eps) - c * (c . g_n) / (len * (len + eps)^2),  g_n = gcos * direction
+    const float gn[3] = {gcos * L.dir[0], gcos * L.dir[1], gcos * L.dir[2]};
+    const float cg = (G.c[0] * gn[0] + G.c[1] * gn[1]) + G.c[2] * gn[2];
+    const float k2 = G.len > 0.0f ? cg * inv * inv / G.len : 0.0f;
+    const float gc[3] = {gn[0] * inv - G.c[0] * k2, gn[1] * inv - G.c[1] * k2, gn[2] * inv - G.c[2] * k2};
+    // c = a x b:  g_a = b x g_c,  g_b = g_c x a;  a = v0 - v1, b = v2 - v1
+    const float ga[3] = {G.b[1] * gc[2] - G.b[2] * gc[1], G.b[2] * gc[0] - G.b[0] * gc[2], G.b[0] * gc[1] - G.b[1] * gc[0]};
+    const float gb[3] = {gc[1] * G.a[2] - gc[2] * G.a[1], gc[2] * G.a[0] - gc[0] * G.a[2], gc[0] * G.a[1] - gc[1] * G.a[0]};
+    float* g0 = grad_vertices + ((size_t)b * Nv + G.i0) * 3;
+    float* g1 = grad_vertices + ((size_t)b * Nv + G.i1) * 3;
+    float* g2 = grad_vertices + ((size_t)b * Nv + G.i2) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        atomicAdd(g0 + k, ga[k]);
+        atomicAdd(g2 + k, gb[k]);
+        atomicAdd(g1 + k, -(ga[k] + gb[k]));
+    }
+}
+
 }  // namespace
 
 extern "C" int nr_b200_vertices_to_faces(const float* vertices, const int32_t* faces, int32_t B, int32_t Nv, int32_t Nf,
@@ -210,6 +306,37 @@ extern "C" int nr_b200_camera_transform_backward(const float* vertices, const fl
         nr_internal::LaunchScope ls("k_camera_bwd", stream);
         k_camera_bwd<<<dim3((unsigned)((Nv + 255) / 256), B), 256, 0, stream>>>(vertices, rot, eye, width, grad_out, Nv, flags,
                                                                                grad_vertices, grad_rot, grad_eye, grad_width);
+    }
+    return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
+}
+
+extern "C" int nr_b200_face_lighting(const float* vertices, const int32_t* faces, const float* light_params, int32_t B,
+                                     int32_t Nv, int32_t Nf, uint32_t flags, float* face_light, void* cuda_stream) {
+    nr_internal::launch_count() = 0;
+    if (!vertices || !faces || !light_params || !face_light || B <= 0 || Nv <= 0 || Nf <= 0 || B > 65535) return NR_ERR_INVALID_ARG;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    {
+        nr_internal::LaunchScope ls("k_face_light_fwd", stream);
+        k_face_light_fwd<<<dim3((unsigned)((Nf + 255) / 256), B), 256, 0, stream>>>(vertices, faces, light_params, Nv, Nf, flags,
+                                                                                   face_light);
+    }
+    return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
+}
+
+extern "C" int nr_b200_face_lighting_backward(const float* vertices, const int32_t* faces, const float* light_params,
+                                              const float* grad_face_light, int32_t B, int32_t Nv, int32_t Nf,
+                                              uint32_t flags, float* grad_vertices, void* cuda_stream) {
+    nr_internal::launch_count() = 0;
+    if (!vertices || !faces || !light_params || !grad_face_light || !grad_vertices || B <= 0 || Nv <= 0 || Nf <= 0 || B > 65535)
+        return NR_ERR_INVALID_ARG;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (!(flags & NR_GRAD_ACCUMULATE) &&
+        cudaMemsetAsync(grad_vertices, 0, (size_t)B * Nv * 3 * sizeof(float), stream) != cudaSuccess)
+        return NR_ERR_CUDA;
+    {
+        nr_internal::LaunchScope ls("k_face_light_bwd", stream);
+        k_face_light_bwd<<<dim3((unsigned)((Nf + 255) / 256), B), 256, 0, stream>>>(vertices, faces, light_params, grad_face_light,
+                                                                                   Nv, Nf, flags, grad_vertices);
     }
     return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
 }

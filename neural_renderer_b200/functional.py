@@ -310,6 +310,65 @@ def face_light(faces, intensity_ambient=0.5, intensity_directional=0.5, color_am
     return light
 
 
+class _FaceLighting(torch.autograd.Function):
+    """face_light [B,F,3] straight from vertices and face indices (nr_b200_face_lighting*); params [C,9], C in {1, B}."""
+
+    @staticmethod
+    def forward(ctx, vertices, faces_i32, params):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        v = vertices.detach().contiguous()
+        bs, nv = v.shape[:2]
+        nf = faces_i32.shape[1]
+        flags = _lib.NR_CAM_SHARED if (params.shape[0] == 1 and bs != 1) else 0
+        out = torch.empty((bs, nf, 3), dtype=torch.float32, device=v.device)
+        with torch.cuda.device(v.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(v.device).cuda_stream)
+            _lib.check(lib.nr_b200_face_lighting(v.data_ptr(), faces_i32.data_ptr(), params.data_ptr(), bs, nv, nf, flags,
+                                                 out.data_ptr(), stream))
+        ctx.save_for_backward(v, faces_i32, params)
+        ctx.flags = flags
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_light):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        v, faces_i32, params = ctx.saved_tensors
+        g = grad_light.detach().to(torch.float32).contiguous()
+        bs, nv = v.shape[:2]
+        grad_v = torch.empty_like(v)
+        with torch.cuda.device(v.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(v.device).cuda_stream)
+            _lib.check(lib.nr_b200_face_lighting_backward(v.data_ptr(), faces_i32.data_ptr(), params.data_ptr(), g.data_ptr(), bs,
+                                                          nv, faces_i32.shape[1], ctx.flags, grad_v.data_ptr(), stream))
+        return grad_v, None, None
+
+
+def face_light_from_vertices(vertices, faces, intensity_ambient=0.5, intensity_directional=0.5, color_ambient=(1, 1, 1),
+                             color_directional=(1, 1, 1), direction=(0, 1, 0)):
+    """`face_light(vertices_to_faces(vertices, faces), ...)` without the gathered tensor: one kernel each way on CUDA."""
+    plain = _is_plain(intensity_ambient, intensity_directional, color_ambient, color_directional, direction)
+    if not (plain and _fused_camera_ok(vertices) and faces.is_cuda):
+        return face_light(vertices_to_faces(vertices, faces), intensity_ambient, intensity_directional, color_ambient,
+                          color_directional, direction)
+    import numpy as np
+    ca, cd, d = (np.asarray(x, dtype=np.float32) for x in (color_ambient, color_directional, direction))
+    if ca.ndim != 1 or cd.ndim != 1 or d.ndim != 1:
+        return face_light(vertices_to_faces(vertices, faces), intensity_ambient, intensity_directional, color_ambient,
+                          color_directional, direction)
+    key = ("light", float(intensity_ambient), float(intensity_directional), tuple(ca.tolist()), tuple(cd.tolist()),
+           tuple(d.tolist()), str(vertices.device))
+    params = _CAMERA_CACHE.get(key)
+    if params is None:
+        row = np.concatenate([np.float32(intensity_ambient) * ca, np.float32(intensity_directional) * cd, d]).astype(np.float32)
+        params = torch.from_numpy(row[None]).to(vertices.device)
+        _CAMERA_CACHE[key] = params
+    return _FaceLighting.apply(vertices, faces.to(torch.int32).contiguous(), params)
+
+
 def lighting(faces, textures, intensity_ambient=0.5, intensity_directional=0.5, color_ambient=(1, 1, 1),
              color_directional=(1, 1, 1), direction=(0, 1, 0)):
     light = face_light(faces, intensity_ambient, intensity_directional, color_ambient, color_directional, direction)

@@ -66,19 +66,18 @@ class Renderer(object):
             faces = torch.cat((faces, faces.flip(2)), dim=1)
             if not fused:
                 textures = torch.cat((textures, textures.permute(0, 1, 4, 3, 2, 5)), dim=1)
-        faces_lighting = F.vertices_to_faces(vertices, faces)
         light_args = (self.light_intensity_ambient, self.light_intensity_directional, self.light_color_ambient,
                       self.light_color_directional, self.light_direction)
         if fused:
             # lighting.py:29-52 and renderer.py:78-80 folded into the sampler: neither `textures * light` nor the
             # doubled texture tensor exists; pixel values are bit-identical to the op-by-op formulation
-            light = F.face_light(faces_lighting, *light_args)
+            light = F.face_light_from_vertices(vertices, faces, *light_args)
             vertices = self._transform(vertices)
             faces = F.vertices_to_faces(vertices, faces)
             return rasterize(
                 faces, textures, self.image_size, self.anti_aliasing, self.near, self.far, self.rasterizer_eps,
                 self.background_color, face_light=light, textures_fill_back=self.fill_back)
-        textures = F.lighting(faces_lighting, textures, *light_args)
+        textures = F.lighting(F.vertices_to_faces(vertices, faces), textures, *light_args)
         vertices = self._transform(vertices)
         faces = F.vertices_to_faces(vertices, faces)
         return rasterize(

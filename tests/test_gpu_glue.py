@@ -114,7 +114,7 @@ def test_renderer_fused_lighting_matches_materialised(teapot, fill_back):
         (img * g).sum().backward()
         results.append((img.detach(), va.grad, ta.grad))
     (img0, gv0, gt0), (img1, gv1, gt1) = results
-    assert torch.equal(img0, img1)
+    assert rel_err(img1.cpu(), img0.cpu()) <= 1e-6  # the light factors differ by fp32 rounding (fused normalisation)
     assert rel_err(gt1.cpu(), gt0.cpu()) <= 1e-5
     assert rel_err(gv1.cpu(), gv0.cpu()) <= 1e-4
 
@@ -149,3 +149,23 @@ def test_face_light_and_fill_back_vs_reference_kernels():
     assert rel_err(fa.grad.cpu(), gf_ref.cpu()) <= 1e-4
     assert rel_err(tb.grad.cpu(), tex_a.grad.cpu()) <= 1e-5
     assert rel_err(lb.grad.cpu(), light_a.grad.cpu()) <= 1e-5
+
+
+def test_face_lighting_kernels(teapot):
+    """nr_b200_face_lighting* against lighting.py's op-by-op formulation (float64 on the CPU), values and gradients."""
+    from neural_renderer_b200 import functional as F
+    dev = torch.device("cuda")
+    v, f = teapot
+    vertices = torch.from_numpy(np.stack([v, v[:, [2, 0, 1]].copy()]))
+    faces = torch.from_numpy(np.stack([f, f]))
+    faces = torch.cat((faces, faces.flip(2)), dim=1)
+    g = torch.randn((2, faces.shape[1], 3), generator=torch.Generator().manual_seed(3))
+    args = (0.3, 0.7, [1.0, 0.9, 0.8], [0.5, 1.0, 0.25], [0.2, 0.9, -0.4])
+    v_ref = vertices.double().requires_grad_(True)
+    ref = F.face_light(F.vertices_to_faces(v_ref, faces), *args)
+    (ref * g.double()).sum().backward()
+    v_gpu = vertices.to(dev).requires_grad_(True)
+    out = F.face_light_from_vertices(v_gpu, faces.to(dev), *args)
+    (out * g.to(dev)).sum().backward()
+    assert rel_err(out.detach().cpu(), ref.detach()) <= 2e-6
+    assert rel_err(v_gpu.grad.cpu(), v_ref.grad) <= 1e-4

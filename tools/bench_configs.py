@@ -100,19 +100,27 @@ def main():
         row.update(ref_fwd_ms=timeit(ref_fwd2, n=5), ref_fwd_bwd_ms=timeit(ref_fb2, n=5))
     out["configs"].append(row)
 
-    # whole Renderer.render call (camera + lighting + gather + rasterize), same shape
-    r = nr.Renderer()
-    r.eye = eye
+    # whole Renderer.render call (camera + lighting + gather + rasterize), same shape: fused glue kernels (camera,
+    # face lighting, lighting / fill_back folded into the sampler) vs the op-by-op torch formulation
     vv = v.clone().requires_grad_(True)
     tt = tex.clone().requires_grad_(True)
+    for fused in (True, False):
+        r = nr.Renderer()
+        r.eye = eye
+        r.fused = fused
 
-    def facade():
-        vv.grad = None
-        tt.grad = None
-        r.render(vv, f, tt).backward(g)
+        def facade():
+            vv.grad = None
+            tt.grad = None
+            r.render(vv, f, tt).backward(g)
 
-    out["configs"].append({"config": "Renderer.render fwd+bwd end to end (torch glue included), teapot 256x256 AA batch 8",
-                           "ours_fwd_bwd_ms": timeit(facade)})
+        def facade_fwd():
+            with torch.no_grad():
+                r.render(vv, f, tt)
+
+        out["configs"].append({"config": "Renderer.render end to end, teapot 256x256 AA batch 8 (%s)"
+                                         % ("fused glue" if fused else "op-by-op torch glue + materialised textures"),
+                               "ours_fwd_ms": timeit(facade_fwd), "ours_fwd_bwd_ms": timeit(facade)})
     print(json.dumps(out, indent=1))
 
 
