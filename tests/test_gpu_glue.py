@@ -169,3 +169,42 @@ def test_face_lighting_kernels(teapot):
     (out * g.to(dev)).sum().backward()
     assert rel_err(out.detach().cpu(), ref.detach()) <= 2e-6
     assert rel_err(v_gpu.grad.cpu(), v_ref.grad) <= 1e-4
+
+
+def test_renderer_step_in_cuda_graph(teapot):
+    """A whole Renderer.render forward + backward (camera, lighting, gather, rasterizer and their backward kernels)
+    only enqueues work on the current stream: it can be captured once and replayed."""
+    import neural_renderer as nr
+    dev = torch.device("cuda")
+    v, f = teapot
+    vertices = torch.from_numpy(np.stack([v, v])).to(dev).requires_grad_(True)
+    faces_idx = torch.from_numpy(np.stack([f, f])).to(dev)
+    tex = torch.rand((2, f.shape[0], 2, 2, 2, 3), generator=torch.Generator().manual_seed(1)).to(dev).requires_grad_(True)
+    g = torch.randn((2, 3, 64, 64), generator=torch.Generator().manual_seed(2)).to(dev)
+    r = nr.Renderer()
+    r.image_size = 64
+    r.eye = nr.get_points_from_angles(2.732, 30, 40)
+
+    def step():
+        vertices.grad = None
+        tex.grad = None
+        img = r.render(vertices, faces_idx, tex)
+        img.backward(g)
+        return img.detach().clone(), vertices.grad.clone(), tex.grad.clone()
+
+    ref = step()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = step()
+    for t in out:
+        t.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], ref[0])
+    assert rel_err(out[1].cpu(), ref[1].cpu()) <= 1e-4 and rel_err(out[2].cpu(), ref[2].cpu()) <= 1e-5

@@ -121,6 +121,26 @@ def main():
         out["configs"].append({"config": "Renderer.render end to end, teapot 256x256 AA batch 8 (%s)"
                                          % ("fused glue" if fused else "op-by-op torch glue + materialised textures"),
                                "ours_fwd_ms": timeit(facade_fwd), "ours_fwd_bwd_ms": timeit(facade)})
+    # the same fused step captured in a CUDA graph (launch latency of the ~14 glue kernels and allocations removed)
+    r = nr.Renderer()
+    r.eye = eye
+
+    def step():
+        vv.grad = None
+        tt.grad = None
+        r.render(vv, f, tt).backward(g)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    out["configs"].append({"config": "Renderer.render fwd+bwd, fused glue, replayed as one CUDA graph",
+                           "ours_fwd_bwd_ms": timeit(graph.replay)})
     print(json.dumps(out, indent=1))
 
 
