@@ -179,6 +179,15 @@ NR_B200_API int nr_b200_face_lighting_backward(const float *vertices, const int3
                                                const float *grad_face_light, int32_t batch_size, int32_t num_vertices,
                                                int32_t num_faces, uint32_t flags, float *grad_vertices, void *cuda_stream);
 
+/* Texture baking of load_obj (reference load_obj.py:88-137): every texel (a, b, c) of the ts^3 cube of face f is the
+ * bilinear sample of `image` [H,W,3] (rows already flipped, load_obj.py:82) at the UV position with barycentric
+ * coordinates (a, b, c) / (a + b + c) of `uv_faces` [F,3,2]; faces with is_update[f] == 0 (is_update may be NULL =
+ * all faces) keep their cube.  Texel (0,0,0) becomes NaN exactly as in the reference (0/0).  `textures`
+ * [F,ts,ts,ts,3] is updated in place. */
+NR_B200_API int nr_b200_bake_textures(const float *image, const float *uv_faces, const int32_t *is_update,
+                                      int32_t num_faces, int32_t texture_size, int32_t image_height,
+                                      int32_t image_width, float *textures, void *cuda_stream);
+
 /* Number of kernels the last forward/backward call on this thread launched (for launch accounting). */
 NR_B200_API int nr_b200_last_launch_count(void);
 

@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = (
     "nr_b200_camera_transform_backward",
     "nr_b200_face_lighting",
     "nr_b200_face_lighting_backward",
+    "nr_b200_bake_textures",
     "nr_b200_last_launch_count",
     "nr_b200_set_profiling",
     "nr_b200_read_profile",
@@ -123,6 +124,8 @@ def load():
     lib.nr_b200_face_lighting_backward.restype = ctypes.c_int
     lib.nr_b200_face_lighting_backward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int32] * 3 + [ctypes.c_uint32, ctypes.c_void_p,
                                                                                                 ctypes.c_void_p]
+    lib.nr_b200_bake_textures.restype = ctypes.c_int
+    lib.nr_b200_bake_textures.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int32] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
     lib.nr_b200_last_launch_count.restype = ctypes.c_int
     lib.nr_b200_set_profiling.restype = None
     lib.nr_b200_set_profiling.argtypes = [ctypes.c_int]

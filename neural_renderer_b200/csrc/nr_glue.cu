@@ -13,6 +13,10 @@
 // Lighting: the per-face RGB factor of lighting.py:29-51 straight from vertices and
 // face indices (no gathered [B,F,3,3] tensor), and its backward as a scatter-add into the vertex gradient.  The
 // factor itself is applied inside the rasterizer's sampler (nr_b200_forward_args.face_light).
+//
+// Texture baking: the bilinear image -> per-face ts^3 cube resampling kernel of
+// load_obj.py:88-137, operation for operation (including its NaN at texel (0,0,0), where the three barycentric
+// coordinates are 0/0).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -244,6 +248,52 @@ __global__ void __launch_bounds__(256) k_face_light_bwd(const float* __restrict_
     }
 }
 
+
+// load_obj.py:97-131.  One thread per texel of every face.  Arithmetic as the reference build evaluates it (read from
+// its SASS): dims = (float)((double)k / (ts - 1.)), normalised by IEEE division with sum = (d0 + d1) + d2;
+// pos = fma(f2, d2, fma(f0, d0, f1 * d1)) * (size - 1); taps blended as fma chains in source order.
+__global__ void __launch_bounds__(256) k_bake_textures(const float* __restrict__ image, const float* __restrict__ uv_faces,
+                                                       const int32_t* __restrict__ is_update, long long n, int ts, int H,
+                                                       int W, float* __restrict__ textures) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t3 = ts * ts * ts;
+    const long long fn = i / t3;
+    if (is_update && __ldg(is_update + fn) == 0) return;
+    const int r = (int)(i - fn * t3);
+    const double den = (double)ts - 1.0;
+    float d0 = (float)((double)((r / (ts * ts)) % ts) / den);
+    float d1 = (float)((double)((r / ts) % ts) / den);
+    float d2 = (float)((double)(r % ts) / den);
+    const float sum = __fadd_rn(__fadd_rn(d0, d1), d2);
+    d0 = __fdiv_rn(d0, sum); d1 = __fdiv_rn(d1, sum); d2 = __fdiv_rn(d2, sum);  // texel (0,0,0): 0/0 = NaN, as in the reference
+    const float* f = uv_faces + fn * 6;
+    const float f0x = __ldg(f), f0y = __ldg(f + 1), f1x = __ldg(f + 2), f1y = __ldg(f + 3), f2x = __ldg(f + 4), f2y = __ldg(f + 5);
+    const float pos_x = __fmul_rn(__fmaf_rn(f2x, d2, __fmaf_rn(f0x, d0, __fmul_rn(f1x, d1))), (float)(W - 1));
+    const float pos_y = __fmul_rn(__fmaf_rn(f2y, d2, __fmaf_rn(f0y, d0, __fmul_rn(f1y, d1))), (float)(H - 1));
+    const int ix = __float2int_rz(pos_x), iy = __float2int_rz(pos_y), iy1 = __float2int_rz(__fadd_rn(pos_y, 1.0f));
+    const float wx1 = __fsub_rn(pos_x, (float)ix), wy1 = __fsub_rn(pos_y, (float)iy);
+    const float wx0 = __fsub_rn(1.0f, wx1), wy0 = __fsub_rn(1.0f, wy1);
+    const float w00 = __fmul_rn(wx0, wy0), w01 = __fmul_rn(wx0, wy1), w10 = __fmul_rn(wx1, wy0), w11 = __fmul_rn(wx1, wy1);
+    // the reference reads one row / column past the image when a coordinate is exactly 1 (weight 0 -- or, when the
+    // float sum pos_y + 1 rounds up, weight ~1: undefined behaviour there); those taps are addressed in bounds here
+    const int cx0 = min(max(ix, 0), W - 1), cx1 = min(max(ix + 1, 0), W - 1);
+    const int cy0 = min(max(iy, 0), H - 1), cy1 = min(max(iy1, 0), H - 1);
+    const float* p00 = image + ((size_t)cy0 * W + cx0) * 3;
+    const float* p01 = image + ((size_t)cy1 * W + cx0) * 3;  // next row, same column
+    const float* p10 = image + ((size_t)cy0 * W + cx1) * 3;  // same row, next column
+    const float* p11 = image + ((size_t)cy1 * W + cx1) * 3;
+    float* out = textures + i * 3;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float c = __fmul_rn(w00, __ldg(p00 + k));
+        c = __fmaf_rn(w01, __ldg(p01 + k), c);
+        c = __fmaf_rn(w10, __ldg(p10 + k), c);
+        c = __fmaf_rn(w11, __ldg(p11 + k), c);
+        out[k] = c;
+    }
+}
+
 }  // namespace
 
 extern "C" int nr_b200_vertices_to_faces(const float* vertices, const int32_t* faces, int32_t B, int32_t Nv, int32_t Nf,
@@ -337,6 +387,19 @@ extern "C" int nr_b200_face_lighting_backward(const float* vertices, const int32
         nr_internal::LaunchScope ls("k_face_light_bwd", stream);
         k_face_light_bwd<<<dim3((unsigned)((Nf + 255) / 256), B), 256, 0, stream>>>(vertices, faces, light_params, grad_face_light,
                                                                                    Nv, Nf, flags, grad_vertices);
+    }
+    return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
+}
+
+extern "C" int nr_b200_bake_textures(const float* image, const float* uv_faces, const int32_t* is_update, int32_t F,
+                                     int32_t ts, int32_t H, int32_t W, float* textures, void* cuda_stream) {
+    nr_internal::launch_count() = 0;
+    if (!image || !uv_faces || !textures || F <= 0 || ts < 2 || H <= 0 || W <= 0) return NR_ERR_INVALID_ARG;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const long long n = (long long)F * ts * ts * ts;
+    {
+        nr_internal::LaunchScope ls("k_bake_textures", stream);
+        k_bake_textures<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(image, uv_faces, is_update, n, ts, H, W, textures);
     }
     return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
 }

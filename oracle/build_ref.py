@@ -74,8 +74,9 @@ def _is_elementwise(call):
             and isinstance(f.value, ast.Attribute) and f.value.attr == "cuda")
 
 
-def collect_call_sites(path=REF_FILE):
+def collect_call_sites(path=REF_FILE, names=None):
     """Return [{name, in_params, out_params, template, keys, lineno}] in source order."""
+    names = KERNEL_NAMES if names is None else names
     with open(path) as f:
         tree = ast.parse(f.read(), path)
     sites = []
@@ -93,8 +94,8 @@ def collect_call_sites(path=REF_FILE):
             sites.append(dict(in_params=in_params, out_params=out_params, template=template, keys=keys,
                               lineno=node.lineno))
     sites.sort(key=lambda s: s["lineno"])
-    assert len(sites) == len(KERNEL_NAMES), "reference layout changed: %d call sites" % len(sites)
-    for s, n in zip(sites, KERNEL_NAMES):
+    assert len(sites) == len(names), "reference layout changed: %d call sites" % len(sites)
+    for s, n in zip(sites, names):
         s["name"] = n
     return sites
 
@@ -179,6 +180,37 @@ def build_one(cfg, sites=None, force=False, keep_ptx=None):
     return out
 
 
+# ---- texture baking kernel of load_obj.py: one binary per (ts, image height, width)
+REF_LOAD_OBJ = os.path.join(REF_ROOT, "neural_renderer", "load_obj.py")
+BAKE_CONFIGS = [(4, 64, 48), (2, 64, 48), (6, 33, 57)]  # (texture_size, image_height, image_width) used by the tests
+
+
+def bake_lib_path(texture_size, image_height, image_width):
+    return os.path.join(OUT_DIR, "nrref_bake_ts%d_%dx%d.so" % (texture_size, image_height, image_width))
+
+
+def build_bake(texture_size, image_height, image_width, force=False, keep_ptx=None):
+    """The reference's bilinear texture-bake kernel string (load_obj.py:88-137), wrapped like the others."""
+    out = bake_lib_path(texture_size, image_height, image_width)
+    if os.path.exists(out) and not force and not keep_ptx:
+        return out
+    os.makedirs(OUT_DIR, exist_ok=True)
+    sites = collect_call_sites(REF_LOAD_OBJ, names=["k_bake"])
+    cfg = dict(image_size=0, num_faces=0, texture_size=int(texture_size), image_height=int(image_height),
+               image_width=int(image_width))
+    src = generate_source(cfg, sites)
+    with tempfile.TemporaryDirectory(prefix="nrref_") as td:
+        cu = os.path.join(td, "bake.cu")
+        with open(cu, "w") as f:
+            f.write(src)
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-shared",
+                        "-Xcompiler", "-fPIC", "-w", "-o", out, cu], check=True)
+        if keep_ptx:
+            subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-w", "-cubin", "-o", keep_ptx, cu],
+                           check=True)
+    return out
+
+
 def build_all(configs, force=False, jobs=None):
     if not os.path.exists(REF_FILE):
         raise FileNotFoundError(REF_FILE)
@@ -195,6 +227,8 @@ def main(argv):
     force = "--force" in argv
     cfgs = all_configs()
     outs = build_all(cfgs, force=force)
+    if os.path.exists(REF_LOAD_OBJ):
+        outs += [build_bake(*c, force=force) for c in BAKE_CONFIGS]
     print("built %d reference kernel libraries under %s" % (len(outs), OUT_DIR))
 
 

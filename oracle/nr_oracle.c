@@ -407,6 +407,50 @@ NRO_API void nro_depth_bwd(const float *faces, const float *depth_map, const int
     }
 }
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Texture baking of load_obj (load_obj.py:88-137).  Same operation order as the reference build evaluates (dims via a
+ * double division rounded to float, IEEE float divisions by (d0 + d1) + d2, pos = fma(f2, d2, fma(f0, d0, f1 * d1)) *
+ * (size - 1), taps blended as an fma chain in source order).  Texel (0,0,0) is 0/0 = NaN like the reference.  The
+ * reference reads one row / column past the image when a coordinate is exactly 1 (with weight 0); here those taps
+ * are clamped into the image.  `image` [H,W,3] is already flipped (load_obj.py:82). */
+NRO_API void nro_bake_textures(const float *image, const float *uv_faces, const int *is_update, int64_t nf, int ts, int H,
+                               int W, float *textures) {
+    const int t3 = ts * ts * ts;
+    const int64_t n = nf * t3;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t fn = i / t3;
+        if (is_update && is_update[fn] == 0) continue;
+        const int r = (int)(i - fn * t3);
+        const double den = (double)ts - 1.0;
+        float d0 = (float)((double)((r / (ts * ts)) % ts) / den);
+        float d1 = (float)((double)((r / ts) % ts) / den);
+        float d2 = (float)((double)(r % ts) / den);
+        const float sum = (d0 + d1) + d2;
+        d0 = d0 / sum; d1 = d1 / sum; d2 = d2 / sum;
+        const float *f = uv_faces + fn * 6;
+        const float pos_x = fmaf(f[4], d2, fmaf(f[0], d0, f[2] * d1)) * (float)(W - 1);
+        const float pos_y = fmaf(f[5], d2, fmaf(f[1], d0, f[3] * d1)) * (float)(H - 1);
+        const int ix = f2i_rz(pos_x), iy = f2i_rz(pos_y), iy1 = f2i_rz(pos_y + 1.0f);
+        const float wx1 = pos_x - (float)ix, wy1 = pos_y - (float)iy;
+        const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+        const float w00 = wx0 * wy0, w01 = wx0 * wy1, w10 = wx1 * wy0, w11 = wx1 * wy1;
+#define NRO_CLAMP(v, hi) ((v) < 0 ? 0 : ((v) > (hi) ? (hi) : (v)))
+        const int cx0 = NRO_CLAMP(ix, W - 1), cx1 = NRO_CLAMP(ix + 1, W - 1);
+        const int cy0 = NRO_CLAMP(iy, H - 1), cy1 = NRO_CLAMP(iy1, H - 1);
+#undef NRO_CLAMP
+        const float *p00 = image + ((int64_t)cy0 * W + cx0) * 3, *p01 = image + ((int64_t)cy1 * W + cx0) * 3;
+        const float *p10 = image + ((int64_t)cy0 * W + cx1) * 3, *p11 = image + ((int64_t)cy1 * W + cx1) * 3;
+        for (int k = 0; k < 3; k++) {
+            float c = w00 * p00[k];
+            c = fmaf(w01, p01[k], c);
+            c = fmaf(w10, p10[k], c);
+            c = fmaf(w11, p11[k], c);
+            textures[i * 3 + k] = c;
+        }
+    }
+}
+
 NRO_API int nro_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -71,6 +71,20 @@ def set_num_threads(n):
     lib().nro_set_num_threads(int(n))
 
 
+def bake_textures(image, uv_faces, is_update, texture_size, textures=None):
+    """load_obj.py:88-137 on the CPU: bilinear image -> per-face cube resampling (image [H,W,3] already flipped)."""
+    image = _f32(image)
+    uv_faces = _f32(uv_faces)
+    nf = uv_faces.shape[0]
+    if textures is None:
+        textures = np.full((nf, texture_size, texture_size, texture_size, 3), 0.5, dtype=np.float32)
+    textures = np.ascontiguousarray(textures, dtype=np.float32)
+    upd = None if is_update is None else np.ascontiguousarray(is_update, dtype=np.int32)
+    lib().nro_bake_textures(_fp(image), _fp(uv_faces), _ip(upd), ctypes.c_int64(nf), int(texture_size), int(image.shape[0]),
+                            int(image.shape[1]), _fp(textures))
+    return textures
+
+
 class OracleRasterize:
     """CPU restatement of the reference `Rasterize` function object (rasterize.py:19-897)."""
 

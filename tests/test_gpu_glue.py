@@ -208,3 +208,68 @@ def test_renderer_step_in_cuda_graph(teapot):
     torch.cuda.synchronize()
     assert torch.equal(out[0], ref[0])
     assert rel_err(out[1].cpu(), ref[1].cpu()) <= 1e-4 and rel_err(out[2].cpu(), ref[2].cpu()) <= 1e-5
+
+
+def _bake_inputs(ts, H, W, F, seed):
+    rng = np.random.default_rng(seed)
+    img = rng.random((H, W, 3), dtype=np.float32)
+    uv = rng.random((F, 3, 2), dtype=np.float32)
+    uv[0] = [[0, 0], [1, 0], [1, 1]]        # exact corners: the one-past-the-edge taps of the reference
+    uv[1] = [[1, 1], [0, 1], [1, 0]]
+    upd = (rng.random(F) < 0.7).astype(np.int32)
+    upd[:2] = 1
+    tex = rng.random((F, ts, ts, ts, 3), dtype=np.float32)
+    return img, uv, upd, tex
+
+
+@pytest.mark.parametrize("cfg", [(4, 64, 48), (2, 64, 48), (6, 33, 57)])
+def test_bake_textures_kernel_bit_exact(cfg):
+    """nr_b200_bake_textures == the C oracle == the reference's own kernel string (load_obj.py:88-137), bit for bit,
+    NaN texels included."""
+    import nr_oracle as o
+    import refbake
+    from neural_renderer_b200 import io
+    ts, H, W = cfg
+    img, uv, upd, tex = _bake_inputs(ts, H, W, 301, seed=ts * 100 + H)
+    got = io.bake_textures(img, uv, upd, ts, tex)
+    want = o.bake_textures(img, uv, upd, ts, tex.copy())
+    # NaN payloads differ between x86 and the GPU; every other value must match bit for bit
+    assert ((got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))).all()
+    assert np.isnan(got).sum() == 3 * int(upd.sum())
+    assert np.array_equal(got[upd == 0], tex[upd == 0])
+    if refbake.available(ts, H, W):
+        dev = torch.device("cuda")
+        ref = refbake.bake(torch.from_numpy(img).to(dev), torch.from_numpy(uv).to(dev), torch.from_numpy(upd).to(dev), ts,
+                           torch.from_numpy(tex).to(dev)).cpu().numpy()
+        same = (got.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(got) & np.isnan(ref))
+        # faces 0 and 1 have UVs of exactly 1: there the reference kernel reads one row past the image -- with weight
+        # 0, or, when (int)(pos_y + 1) rounds up past (int)pos_y + 1, with weight ~1 (undefined in the reference); the
+        # product addresses those taps inside the image, so only the in-bounds faces are compared
+        assert same[2:].all()
+    else:
+        pytest.skip("reference bake kernel not built (compared with the C oracle only)")
+
+
+def test_load_obj_with_textures_and_render():
+    """examples 1 / 4 call sequence on a textured OBJ: load_obj(load_texture=True) -> Renderer.render."""
+    import os
+    import neural_renderer as nr
+    import nr_oracle as o
+    from neural_renderer_b200 import io
+    obj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "textured", "quads.obj")
+    v, f, tex = nr.load_obj(obj, texture_size=4, load_texture=True)
+    # host composition with the oracle in place of the kernel
+    uv, names = io.parse_texture_faces(obj)
+    want = np.full((6, 4, 4, 4, 3), 0.5, dtype=np.float32)
+    want[1:4] = np.float32([0.2, 0.4, 0.6])
+    want[4:] = np.float32([0.9, 0.1, 0.3])
+    img = io._read_image(os.path.join(os.path.dirname(obj), "pattern.png"))[::-1]
+    want = o.bake_textures(img, uv, (np.array(names) == "painted").astype(np.int32), 4, want)
+    assert ((tex.view(np.uint32) == want.view(np.uint32)) | (np.isnan(tex) & np.isnan(want))).all()
+    dev = torch.device("cuda")
+    r = nr.Renderer()
+    r.image_size = 64
+    r.eye = nr.get_points_from_angles(2.732, 20, 30)
+    image = r.render(torch.from_numpy(v)[None].to(dev), torch.from_numpy(f)[None].to(dev), torch.from_numpy(tex)[None].to(dev))
+    assert image.shape == (1, 3, 64, 64) and torch.isfinite(image).all()  # texel (0,0,0) (NaN) is never sampled at ts = 4
+    assert float(image.max()) > 0.1
