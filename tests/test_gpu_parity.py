@@ -422,7 +422,7 @@ def test_cuda_graph_capture_and_side_stream():
 
 
 def test_examples_optimise():
-    """The reference's example 2 / 3 call sequences (torch instead of Chainer) make progress end to end."""
+    """The reference's example 2 / 3 / 4 call sequences (torch instead of Chainer) make progress end to end."""
     import importlib.util
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -432,6 +432,13 @@ def test_examples_optimise():
         spec.loader.exec_module(mod)
         losses = mod.run(iters)
         assert np.isfinite(losses).all() and losses[-1] < 0.8 * losses[0], (name, losses[0], losses[-1])
+    # example 4: the camera position is the parameter (gradients through the fused camera kernel)
+    spec = importlib.util.spec_from_file_location("example4", os.path.join(root, "examples", "example4_optimize_camera.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    losses, eye = mod.run(150)
+    assert np.isfinite(losses).all() and np.isfinite(eye).all()
+    assert min(losses) < 0.9 * losses[0], (losses[0], min(losses))
 
 
 def test_edge_cases():
