@@ -294,6 +294,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     distributed = world > 1
+    # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     w = WORKLOAD
     B, F, S, ts = w["batch_per_gpu"], w["num_faces"], w["image_size"], w["texture_size"]
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
