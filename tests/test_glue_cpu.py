@@ -77,3 +77,45 @@ def test_batch_sharding_two_ranks_gloo():
     assert [(r[1], r[2]) for r in res] == [(0, 5), (5, 10)]  # contiguous, disjoint, complete
     assert res[0][3] == [10.0] * 4 and res[1][3] == [10.0] * 4
     assert res[0][4] == 2.0  # max over ranks (timing reduction)
+
+
+def test_camera_transform_composes_look_at_and_perspective():
+    """functional.camera_transform (what Renderer._transform calls) on CPU tensors == look_at / look followed by
+    perspective, and differentiates with respect to a tensor eye (examples/example4 call sequence)."""
+    import torch
+    from neural_renderer_b200 import functional as F
+    gen = torch.Generator().manual_seed(3)
+    v = torch.rand((2, 40, 3), generator=gen, dtype=torch.float64) - 0.5
+    eye = [0.4, 0.9, -2.5]
+    assert torch.allclose(F.camera_transform(v, eye), F.perspective(F.look_at(v, eye), 30.))
+    assert torch.allclose(F.camera_transform(v, eye, "look", [0.1, 0.0, 1.0], False), F.look(v, eye, [0.1, 0.0, 1.0]))
+    assert torch.equal(F.camera_transform(v, eye, "none", None, False), v)
+    e = torch.tensor(eye, dtype=torch.float64, requires_grad=True)
+    F.camera_transform(v, e).sum().backward()
+    assert e.grad is not None and torch.isfinite(e.grad).all() and float(e.grad.abs().sum()) > 0
+
+
+def test_face_light_is_the_factor_of_lighting(teapot):
+    """lighting(faces, textures) == textures * face_light(faces) (lighting.py:29-52), and
+    face_light_from_vertices(vertices, faces) == face_light(vertices_to_faces(vertices, faces)) on the CPU path."""
+    import torch
+    from neural_renderer_b200 import functional as F
+    v, f = teapot
+    vertices = torch.from_numpy(v)[None]
+    faces = torch.from_numpy(f)[None]
+    tex = torch.rand((1, f.shape[0], 2, 2, 2, 3), generator=torch.Generator().manual_seed(4))
+    args = (0.4, 0.6, [1.0, 0.9, 0.8], [0.3, 1.0, 0.5], [0.0, 0.8, -0.6])
+    fw = F.vertices_to_faces(vertices, faces)
+    light = F.face_light(fw, *args)
+    assert light.shape == (1, f.shape[0], 3) and float(light.min()) >= 0.4 * 0.8 - 1e-6
+    assert torch.equal(F.lighting(fw, tex, *args), tex * light[:, :, None, None, None, :])
+    assert torch.equal(F.face_light_from_vertices(vertices, faces, *args), light)
+
+
+def test_obj_roundtrip(tmp_path, teapot):
+    from neural_renderer_b200 import io
+    v, f = teapot
+    path = str(tmp_path / "t.obj")
+    io.save_obj(path, v, f)
+    v2, f2 = io.load_obj(path, normalization=False)
+    assert np.array_equal(f2, f) and np.allclose(v2, v, atol=1e-6)
