@@ -746,6 +746,10 @@ BinLayout bin_layout(int B, int F, int S, int rec_bytes) {
     if (const char* env = getenv("NR_B200_STRIP_KB")) strip_bytes = (size_t)atoi(env) * 1024;  // tuning knob
     int W = kMaxLines;
     while (W > 1 && (size_t)W * ((S + 1) & ~1) * rec_bytes > strip_bytes) W >>= 1;
+    // one-line strips pay the per-CTA front end (staging, face list, task sort) per line: two lines are worth twice
+    // the shared memory up to 32 KB (raster 512: 3.5 -> 3.3 ms at the Renderer-default shape, 4.3 -> 3.2 ms at 70 k
+    // faces); beyond that the lost occupancy costs more (measured with 64 KB)
+    if (W == 1 && !getenv("NR_B200_STRIP_KB") && (size_t)2 * ((S + 1) & ~1) * rec_bytes <= 2 * (size_t)kStripBytesDefault) W = 2;
     L.W = W;
     L.w_log2 = 0;
     while ((1 << L.w_log2) < W) L.w_log2++;
