@@ -86,3 +86,30 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "nr_oracle" not in src and "refhost" not in src and "oracle/" not in src, f
+
+
+def test_glue_entry_points_reject_null_arguments(lib):
+    # every glue entry point validates its arguments on the host before any launch
+    assert lib.nr_b200_vertices_to_faces(None, None, 1, 1, 1, None, None) == -1
+    assert lib.nr_b200_camera_transform(None, None, None, None, 1, 1, 0, None, None) == -1
+    assert lib.nr_b200_camera_transform_backward(None, None, None, None, None, 1, 1, 0, None, None, None, None, None) == -1
+    assert lib.nr_b200_face_lighting(None, None, None, 1, 1, 1, 0, None, None) == -1
+    assert lib.nr_b200_face_lighting_backward(None, None, None, None, 1, 1, 1, 0, None, None) == -1
+    assert lib.nr_b200_bake_textures(None, None, None, 1, 4, 8, 8, None, None) == -1
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sizeof / offsetof of the two argument structs as a C compiler sees include/nr_b200.h == the ctypes mirror."""
+    import subprocess
+    from neural_renderer_b200 import _lib
+    src = tmp_path / "s.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nr_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(nr_b200_forward_args), offsetof(nr_b200_forward_args, faces), offsetof(nr_b200_forward_args, face_light),'
+                   'sizeof(nr_b200_backward_args), offsetof(nr_b200_backward_args, faces), offsetof(nr_b200_backward_args, grad_face_light));'
+                   'return 0;}\n')
+    exe = tmp_path / "s"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_lib.ForwardArgs), _lib.ForwardArgs.faces.offset, _lib.ForwardArgs.face_light.offset,
+            ctypes.sizeof(_lib.BackwardArgs), _lib.BackwardArgs.faces.offset, _lib.BackwardArgs.grad_face_light.offset]
+    assert got == want
