@@ -111,7 +111,14 @@ def _fused_camera_ok(vertices):
     return vertices.is_cuda and vertices.dtype == torch.float32 and vertices.shape[0] <= 65535
 
 
-_CAMERA_CACHE = {}
+_CAMERA_CACHE = {}  # small device constants (camera frames, tan(angle), light parameters) keyed by their host values
+
+
+def _cache_put(key, value):
+    if len(_CAMERA_CACHE) >= 256:  # bounded: a caller that animates the camera / light with Python floats must not leak
+        _CAMERA_CACHE.clear()
+    _CAMERA_CACHE[key] = value
+    return value
 
 
 def _host_camera(kind, eye, aux, up, device):
@@ -134,10 +141,7 @@ def _host_camera(kind, eye, aux, up, device):
     y_axis = normalize(np.cross(z_axis, x_axis).astype(f32))
     rot = torch.from_numpy(np.stack((x_axis, y_axis, z_axis))[None].astype(f32)).to(device)
     eye_t = torch.from_numpy(e[None]).to(device)
-    if len(_CAMERA_CACHE) > 256:
-        _CAMERA_CACHE.clear()
-    _CAMERA_CACHE[key] = (rot, eye_t)
-    return rot, eye_t
+    return _cache_put(key, (rot, eye_t))
 
 
 def _is_plain(*vals):
@@ -182,8 +186,7 @@ def _perspective_width(vertices, angle):
         hit = _CAMERA_CACHE.get(key)
         if hit is None:
             a = torch.tensor(float(angle), dtype=vertices.dtype, device=vertices.device) / 180. * 3.1416
-            hit = torch.tan(a)[None]
-            _CAMERA_CACHE[key] = hit
+            hit = _cache_put(key, torch.tan(a)[None])
         return hit
     angle = angle / 180. * 3.1416
     angle = angle[None] if angle.dim() == 0 else angle
@@ -364,8 +367,7 @@ def face_light_from_vertices(vertices, faces, intensity_ambient=0.5, intensity_d
     params = _CAMERA_CACHE.get(key)
     if params is None:
         row = np.concatenate([np.float32(intensity_ambient) * ca, np.float32(intensity_directional) * cd, d]).astype(np.float32)
-        params = torch.from_numpy(row[None]).to(vertices.device)
-        _CAMERA_CACHE[key] = params
+        params = _cache_put(key, torch.from_numpy(row[None]).to(vertices.device))
     return _FaceLighting.apply(vertices, faces.to(torch.int32).contiguous(), params)
 
 
