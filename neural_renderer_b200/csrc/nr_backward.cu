@@ -93,10 +93,64 @@ __device__ __forceinline__ float load_grad(const float* g, bool aa, int S, size_
 // storage at kWideStrips entries per face and axis.
 constexpr int kWideStrips = 8;
 
+constexpr int kBinSmemStrips = 2048;  // strips (+1 wide slot) per axis whose counters fit the CTA's shared memory
+
+// One CTA = 256 consecutive faces of one item.  The faces are first counted per strip in SHARED memory (neighbouring
+// faces hit the same few strips: native shared-memory integer atomics instead of contended global ones); the CTA then
+// touches every non-empty global counter / cursor ONCE to publish its count (kFill = false) or to reserve its range of
+// the list (kFill = true), and the faces are written at reserved base + local rank.
 template <bool kFill>
 __global__ void __launch_bounds__(256) k_strip_bin(const uint2* __restrict__ bbox, int F, int w_log2, int nstrips,
                                                    int* __restrict__ cnt, const int* __restrict__ off,
                                                    int* __restrict__ cursor, int* __restrict__ list) {
+    extern __shared__ int s_bin[];  // [2][nstrips + 1] local counts, then (fill) [2][nstrips + 1] reserved bases
+    const int b = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nslots = 2 * (nstrips + 1);
+    int* s_cnt = s_bin;
+    int* s_base = s_bin + nslots;
+    for (int i = threadIdx.x; i < nslots; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    uint2 bb = make_uint2(pack16(1, 0), pack16(1, 0));
+    if (f < F) bb = __ldg(bbox + (size_t)b * F + f);
+    const bool active = unpack_lo(bb.x) <= unpack_hi(bb.x);  // culled faces carry an empty box
+    int slot0[2], nslot[2];
+    int rank[2][kWideStrips];
+#pragma unroll
+    for (int axis = 0; axis < 2; axis++) {
+        const uint32_t v = axis == 0 ? bb.x : bb.y;
+        const int s_lo = unpack_lo(v) >> w_log2, s_hi = unpack_hi(v) >> w_log2;
+        const bool wide = s_hi - s_lo + 1 > kWideStrips;
+        slot0[axis] = axis * (nstrips + 1) + (wide ? nstrips : s_lo);
+        nslot[axis] = active ? (wide ? 1 : s_hi - s_lo + 1) : 0;
+#pragma unroll
+        for (int k = 0; k < kWideStrips; k++) {
+            rank[axis][k] = 0;
+            if (k < nslot[axis]) rank[axis][k] = atomicAdd(&s_cnt[slot0[axis] + k], 1);
+        }
+    }
+    __syncthreads();
+    const size_t gbase = (size_t)b * nslots;
+    for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
+        const int c = s_cnt[i];
+        if (c == 0) continue;
+        if (!kFill) atomicAdd(cnt + gbase + i, c);
+        else s_base[i] = off[gbase + i] + atomicAdd(cursor + gbase + i, c);
+    }
+    if (!kFill) return;
+    __syncthreads();
+#pragma unroll
+    for (int axis = 0; axis < 2; axis++)
+#pragma unroll
+        for (int k = 0; k < kWideStrips; k++)
+            if (k < nslot[axis]) list[s_base[slot0[axis] + k] + rank[axis][k]] = f;
+}
+
+// The same binning with global atomics only, for rasters with more strips than the shared-memory counters hold.
+template <bool kFill>
+__global__ void __launch_bounds__(256) k_strip_bin_global(const uint2* __restrict__ bbox, int F, int w_log2, int nstrips,
+                                                          int* __restrict__ cnt, const int* __restrict__ off,
+                                                          int* __restrict__ cursor, int* __restrict__ list) {
     const int b = blockIdx.y;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
@@ -843,9 +897,12 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
         if (cudaMemsetAsync(cnt, 0, L.off_list - L.off_cnt, stream) != cudaSuccess) return NR_ERR_CUDA;  // counters, offsets, cursors
         {
             const dim3 g((F + 255) / 256, B);
+            const bool bin_smem = nstrips + 1 <= kBinSmemStrips && !getenv("NR_B200_BIN_GLOBAL");
+            const size_t bin_bytes = (size_t)4 * (nstrips + 1) * sizeof(int);
             {
                 nr_internal::LaunchScope ls("k_strip_bin", stream);
-                k_strip_bin<false><<<g, 256, 0, stream>>>(bbox, F, L.w_log2, nstrips, cnt, nullptr, nullptr, nullptr);
+                if (bin_smem) k_strip_bin<false><<<g, 256, bin_bytes, stream>>>(bbox, F, L.w_log2, nstrips, cnt, nullptr, nullptr, nullptr);
+                else k_strip_bin_global<false><<<g, 256, 0, stream>>>(bbox, F, L.w_log2, nstrips, cnt, nullptr, nullptr, nullptr);
             }
             {
                 nr_internal::LaunchScope ls("k_strip_scan", stream);
@@ -853,7 +910,8 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
             }
             {
                 nr_internal::LaunchScope ls("k_strip_bin", stream);
-                k_strip_bin<true><<<g, 256, 0, stream>>>(bbox, F, L.w_log2, nstrips, cnt, off, cursor, list);
+                if (bin_smem) k_strip_bin<true><<<g, 256, bin_bytes, stream>>>(bbox, F, L.w_log2, nstrips, cnt, off, cursor, list);
+                else k_strip_bin_global<true><<<g, 256, 0, stream>>>(bbox, F, L.w_log2, nstrips, cnt, off, cursor, list);
             }
         }
         p.strip_cnt = cnt; p.strip_off = off; p.strip_list = list;
