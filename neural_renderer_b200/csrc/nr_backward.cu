@@ -64,6 +64,7 @@ struct BwdParams {
     float eps, two_over_S, tex_cmp, tex_val;
 };
 
+//@phase helpers: rcp / vector RED / load_grad (inlined)
 // MUFU.RCP (about 1 ulp): the edge-scan terms are held to 1e-4 relative, not to bit-exactness
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(256) k_strip_scan(const int* __restrict__ cnt,
 }
 
 // ------------------------------------------------------------------------------------------------ k_edge_scan
+//@phase packed f32x2 helpers (the out-scan's math is attributed here)
 // packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): two pixels of a scan advance per instruction
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
@@ -231,6 +233,7 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f
 //   R[pp] = {ga_e, ga_o}             only when both rgb and alpha gradients exist (kMode == 3)
 //   ci[i] = {I0, I1, I2, fim}        colours and face index per pixel: task set-up and the short in-scan only
 // kMode: 1 = rgb, 2 = alpha only (g0 = g_alpha, I0 = alpha), 3 = rgb + alpha
+//@phase prologue
 template <int kMode, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const __grid_constant__ BwdParams p) {
     constexpr int kFaceQueue = 2 * kThreads, kTaskCap = 8 * kThreads;
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
     const bool aa = (p.flags & NR_ANTI_ALIASING) != 0;
     const size_t plane = (size_t)S * S;
 
+    //@phase 1 stage strip
     // ---- 1. stage the strip (image orientation in global memory: raster row y is stored at row S-1-y).
     //         One thread per pixel PAIR of a line: 16-byte shared-memory stores, half the index arithmetic.
     struct Px { float A, g0, g1, g2, ga; float4 c; };
@@ -308,6 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
     const float fS = (float)S;
     const int lhi = l0 + nlines - 1;
 
+    //@phase task_setup (inlined into 2b and 3)
     // Geometry of one (face, edge, line) scan, evaluated exactly as rasterize.py:545-609 / :662-672 does.
     struct Task {
         float d1_cross, k0, k1;  // dist_v = (d1 - d1_cross) * k_v  (k_v = ratio_v * 2 / S), +-eps
@@ -361,6 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
         T.in_from = max(min(T.d1_in, lim2), 0);
         T.in_to = min(max(T.d1_in, lim2), S - 1);
     };
+    //@phase scalar visit (in-scan)
     // scalar visit (in-scan, and out-scans of the rare tasks with a vertex exactly on the line)
     auto visit = [&](const Task& T, int line, int d1, float r0, float r1, float r2, float ra, float& acc0, float& acc1) {
         const size_t pi = (size_t)line * npair + (d1 >> 1);
@@ -386,6 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
         }
     };
 
+    //@phase 2a face lists
     const int len_shift = p.len_shift;  // scan length >> len_shift indexes 32 sort buckets
     // faces are queued until the next batch of kThreads could overflow the face queue or the task expansion
     const int cap_faces = min(kFaceQueue, kTaskCap / (3 * nlines));
@@ -427,6 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
         // the queue may hold more faces than one expansion round can take (cap_faces < kThreads for wide strips)
         for (int q0 = 0; q0 < nface; q0 += cap_faces) {
             const int nq = min(cap_faces, nface - q0);
+            //@phase 2b expand + sort
             // ---- 2b. expand (face, edge, line) slots; valid ones become tasks bucketed by scan length
             for (int i = tid; i < nq * 3; i += kThreads) {
                 const int e = i % 3, q = q0 + i / 3;
@@ -468,6 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
             }
             __syncthreads();
 
+            //@phase 3 batches: set-up + in-scan
             // ---- 3. warps pull batches of 32 tasks of similar length.  Every lane sets up its own task and runs the
             //         short in-scan; the long out-scans are then swept by 4 lanes per task (8 tasks at a time), two
             //         pixels per lane and step (packed f32x2 math, 16-byte shared-memory loads).
@@ -508,6 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                     if (!fast)
                         for (int d1 = T.out_from; d1 <= T.out_to; d1++) visit(T, line, d1, c0, c1, c2, ca, acc0, acc1);
                 }
+                //@phase 3 out-scan passes
                 // along an out-scan (d1 - d1_cross) keeps the sign of dir, so the sign of eps is fixed per vertex
                 const float fdir = (float)T.dir;
                 const float e0 = (fdir * T.k0 > 0.0f) ? p.eps : -p.eps, e1 = (fdir * T.k1 > 0.0f) ? p.eps : -p.eps;

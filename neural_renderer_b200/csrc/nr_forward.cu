@@ -102,6 +102,7 @@ __device__ __forceinline__ void face_record(const FwdParams& p, int b, int fn, f
     z[0] = c[2]; z[1] = c[5]; z[2] = c[8];
 }
 
+//@phase shade (resolve helper)
 struct Shaded {
     int fim;
     float w0, w1, w2, depth, r, g, b, alpha;
@@ -170,6 +171,7 @@ __device__ __forceinline__ Shaded shade_pixel(const FwdParams& p, const float (*
     return o;
 }
 
+//@phase prologue
 template <bool kAA, int kTL2, int kThreads>
 __global__ void __launch_bounds__(kThreads, kTL2 == 65 ? 1024 / kThreads : 1) k_raster_tile(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, kTL2 == 65 ? 1024 / kThreads : 1) k_
     const int ngroups = p.ngroups;
     const uint32_t lt_mask = (1u << lane) - 1u;
     for (int gbase = 0; gbase < ngroups; gbase += kLiveCap) {
+        //@phase group cull
         // ---- group cull, one group (32 consecutive faces) per thread: the groups whose union box overlaps the tile
         //      are queued in shared memory, so the warps below only ever touch faces near the tile
         if (tid == 0) { sm.live_count = 0; sm.next_group = 0; }
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, kTL2 == 65 ? 1024 / kThreads : 1) k_
         }
         __syncthreads();
         const int nlive = sm.live_count;
+        //@phase group pull + face cull + survivor records
         // ---- warp-autonomous: pull live groups
         const uint2* bbox = p.bbox + (size_t)b * p.F;
         float(*ring)[kRingWords] = sm.ring[warp];
@@ -277,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, kTL2 == 65 ? 1024 / kThreads : 1) k_
                                      ((uint32_t)(by1 - ty0) << 24);
                 r4[1] = make_float4(c[6], c[7], __uint_as_float(((uint32_t)f << 10) | rec), __uint_as_float(box));
             }
+            //@phase row spans (prefix, owner search, edge binary searches)
             // ---- row-span rasterization.  For a fixed pixel row each edge test  r_k < (xp - x_k) * dy_k  is monotone in
             //      x (xp increases with x; rounded subtraction and multiplication are monotone), so the pixels that
             //      pass all three tests form one interval [lo, hi].  Its ends are found by binary search with the
@@ -334,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, kTL2 == 65 ? 1024 / kThreads : 1) k_
                         if (neg) lo = a2; else hi = a2 - 1;
                     }
                 }
+                //@phase fragments (flatten, weights + depth, z-min)
                 // flatten the 32 spans into fragments
                 const int n = max(hi - lo + 1, 0);
                 int sincl = n;
@@ -387,6 +393,7 @@ __global__ void __launch_bounds__(kThreads, kTL2 == 65 ? 1024 / kThreads : 1) k_
         __syncthreads();  // every fragment of this pass is in the z-tile; the group queue may be rebuilt
     }
 
+    //@phase resolve + stores
     // ------------------------------------------------------------------ resolve + shade + stream out
     const int S = p.S;
     float bgr = p.bg[0], bgg = p.bg[1], bgb = p.bg[2];

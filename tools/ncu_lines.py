@@ -59,6 +59,9 @@ def main():
     ap.add_argument("--so", default="neural_renderer_b200/libnr_b200.so")
     ap.add_argument("--top", type=int, default=30)
     ap.add_argument("--launch", type=int, default=0, help="index among the launches of this kernel in the report")
+    ap.add_argument("--phases", action="store_true",
+                    help="also aggregate by the `//@phase <label>` comment markers of the source files (a marker labels "
+                         "every line up to the next marker of the same file)")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     # the CSV holds one block per launch: "Kernel Name",<name> / header / rows
@@ -107,6 +110,38 @@ def main():
                     return src_cache[p][l - 1].strip()[:90]
         return ""
 
+    if a.phases:
+        markers = {}  # file -> sorted [(line, label)]
+
+        def phase_of(f, l):
+            if f not in markers:
+                ms = []
+                for root in (".", "neural_renderer_b200/csrc"):
+                    pth = os.path.join(root, f)
+                    if os.path.exists(pth):
+                        for k, text in enumerate(open(pth).read().splitlines(), 1):
+                            m = re.search(r"//@phase\s+(.*)", text)
+                            if m:
+                                ms.append((k, m.group(1).strip()))
+                        break
+                markers[f] = ms
+            label = "(unmarked)"
+            for k, lab in markers[f]:
+                if k <= l:
+                    label = lab
+                else:
+                    break
+            return "%s: %s" % (f, label)
+
+        ph = defaultdict(lambda: [0, 0])
+        for (f, l), (ie, ti, sm) in agg.items():
+            g = ph[phase_of(f, l)]
+            g[0] += ie
+            g[1] += sm
+        print("%-78s %8s %8s" % ("phase", "inst %", "samp %"))
+        for name, (ie, sm) in sorted(ph.items(), key=lambda kv: -kv[1][0]):
+            print("%-78s %7.2f%% %7.2f%%" % (name[:78], 100.0 * ie / max(tot_i, 1), 100.0 * sm / max(tot_s, 1)))
+        print()
     print("%-22s %8s %8s %6s  %s" % ("file:line", "inst %", "samp %", "lanes", "source"))
     for (f, l), (ie, ti, sm) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:a.top]:
         print("%-22s %7.2f%% %7.2f%% %6.1f  %s" % ("%s:%d" % (f, l), 100.0 * ie / max(tot_i, 1), 100.0 * sm / max(tot_s, 1),
