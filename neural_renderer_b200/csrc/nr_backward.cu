@@ -2,20 +2,27 @@
 //
 // Replaces Rasterize.backward_gpu (reference neural_renderer/rasterize.py:849-889):
 //
+//   k_strip_bin /     pre-pass of K5: every front face is appended to the list of each W-line strip (per axis) that
+//   k_strip_scan      its pixel box overlaps -- count, exclusive scan per (item, axis), fill; counted per CTA in shared
+//                     memory first.  Faces spanning more than kWideStrips strips go to one "wide" list per item / axis.
 //   k_edge_scan       K5, the approximate-gradient image scan (rasterize.py:528-748).  The reference runs one thread
-//                     per face that walks image columns/rows straight out of global memory.  Here a CTA owns a strip
-//                     of W image lines (columns for axis 0, rows for axis 1) of one batch item, stages the strip's
-//                     pixels once in shared memory as 32-byte records {I_rgb, dL/dI_rgb, dL/dalpha, face index}
-//                     (transposed for axis 0 so that every scan walks contiguous shared memory), culls faces against
-//                     the strip with the forward pass's chunk / face boxes, compacts the surviving
-//                     (face, edge, line) scan tasks into a shared queue, and runs one task per lane.  Each task
+//                     per face that walks image columns / rows straight out of global memory.  Here a CTA owns a strip
+//                     of W image lines (columns for axis 0, rows for axis 1) of one batch item and stages it once in
+//                     shared memory as pixel PAIRS {A, g0 | g1, g2} with A = sum_c I_c * g_c (every scan walks
+//                     contiguous shared memory; diff_grad = A - sum_c ref_c * g_c).  The strip's face list is expanded
+//                     into (face, edge, line) tasks, counting-sorted by scan length and pulled by warps in batches of
+//                     32: every lane sets up its own task and runs the short in-scan; the long out-scans are swept by
+//                     4 lanes per task, two pixels per lane and step, with packed fp32 math (FFMA2).  Each task
 //                     reproduces the reference's discrete decisions exactly (crossing pixel floor/ceil, the
 //                     `face_index_map == fn` gates, the in-scan limit) and accumulates the same
 //                     -relu(dI . dL/dI) / dist terms; only the summation order differs (fp32 atomics into grad_faces).
 //   k_texture_grad    K6 (rasterize.py:760-792): the 8 trilinear weights/indices are recomputed from the saved
 //                     weight/depth maps with the forward expression tree instead of being stored (64 B/pixel in the
-//                     reference) and scattered with float atomics.
-//   k_depth_grad      K7 (rasterize.py:805-847): analytic d zp / d(x, y, z) of the winning face.
+//                     reference) and scattered with vector float reductions (red.global.add.v2/v4.f32); applies the
+//                     per-face light factor / fill_back cube sharing of the forward sampler and reduces d loss /
+//                     d face_light per run of lanes.
+//   k_depth_grad      K7 (rasterize.py:805-847): analytic d zp / d(x, y, z) of the winning face, summed per run of
+//                     neighbouring lanes that show the same face before the atomics.
 //
 // Upstream gradients arrive in API layout (planar, image orientation, pooled by 2x2 when anti-aliasing): the
 // backward of rasterize_rgbad's transpose / flip / average pooling (rasterize.py:953-969) is folded into the loads.
