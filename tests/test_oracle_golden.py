@@ -115,3 +115,37 @@ def test_depth_gradient_matches_finite_differences():
             lm = (o.rasterize_depth(fm, 64, False)["depth"][0, py, px] - 1) ** 2
             num[0, 0, k, l] = (lp - lm) / (2 * h)
     np.testing.assert_allclose(gf, num, atol=2e-3)
+
+
+def test_row_coverage_is_one_interval_in_fp32():
+    """The forward kernel's row-span rasterization rests on this: for a fixed pixel row every edge test of the
+    reference, (yp - y_k) * dx_k < (xp - x_k) * dy_k evaluated in fp32 (sub, sub, mul -- never fused), flips at most
+    once along x, so the pixels that pass all three tests form ONE interval.  Checked here by brute force over random
+    and adversarial triangles (tiny, huge, nearly degenerate, vertices on pixel centres) with numpy's IEEE float32."""
+    rng = np.random.default_rng(2024)
+    f32 = np.float32
+    for S in (17, 64, 256):
+        xs = ((2 * np.arange(S) + 1 - S).astype(np.float64) / S).astype(f32)          # rasterize.py:291-292
+        n = 1500
+        scale = rng.choice([1e-3, 3e-2, 0.3, 1.0, 5.0, 50.0], size=(n, 1, 1))
+        tri = (rng.uniform(-1, 1, size=(n, 1, 2)) + scale * rng.uniform(-1, 1, size=(n, 3, 2))).astype(f32)
+        tri[:50, :, 0] = xs[rng.integers(0, S, size=(50, 3))]                          # vertices exactly on pixel centres
+        tri[50:100, :, 1] = xs[rng.integers(0, S, size=(50, 3))]
+        tri[100:130, 2] = tri[100:130, 1] + f32(1e-6) * (tri[100:130, 0] - tri[100:130, 1])   # slivers
+        for t in tri:
+            x0, y0, x1, y1, x2, y2 = t[0, 0], t[0, 1], t[1, 0], t[1, 1], t[2, 0], t[2, 1]
+            yp = xs[:, None]                                                            # rows
+            xp = xs[None, :]                                                            # columns
+            edges = ((x0, y0, x1 - x0, y1 - y0), (x1, y1, x2 - x1, y2 - y1), (x2, y2, x0 - x2, y0 - y2))
+            inside = np.ones((S, S), dtype=bool)
+            for (xe, ye, dx, dy) in edges:
+                out = ((yp - ye) * dx) < ((xp - xe) * dy)                               # [rows, cols], fp32 throughout
+                flips = (out[:, 1:] != out[:, :-1]).sum(axis=1)
+                assert flips.max() <= 1                                                 # monotone along x
+                if flips.any():
+                    # the direction of the flip is the sign of dy, as the kernel's binary search assumes
+                    r = int(np.argmax(flips))
+                    assert out[r, -1] == (dy >= 0)
+                inside &= ~out
+            runs = (inside[:, 1:] != inside[:, :-1]).sum(axis=1) + inside[:, 0] + inside[:, -1]
+            assert runs.max() <= 2                                                      # covered pixels: one interval per row
