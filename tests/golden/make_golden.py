@@ -11,6 +11,10 @@ tree, so tests read only the small files this script writes next to itself:
                                         test_rasterize_depth.py:31-35)
                         depth_u8     : tests/data/test_depth.png          (test_rasterize_depth.py:39-58)
                         rasterize1_u8, rasterize2_u8 : the un-asserted snapshots test_rasterize.py:15-50 writes
+  display/              the small textured model of test_load_obj.py:55-62 (tests/data/4e49.../model.obj, 3644 faces,
+                        7 materials, 2 texture images), RE-SERIALISED by this script from the parsed arrays (model.obj
+                        / model.mtl / texture*.png, lossless PNG of the decoded JPEGs) plus display_u8.npz = the
+                        tests/data/display.png the reference's test writes for it (never asserted there)
   kat.json              the two known-answer gradient cases of test_rasterize_silhouettes.py:37-99 /
                         test_rasterize.py:76-149 (numbers are test facts quoted from those files)
 """
@@ -57,7 +61,52 @@ def main():
     }
     with open(os.path.join(HERE, "kat.json"), "w") as f:
         json.dump(kat, f, indent=1)
+    write_display_fixture(data)
     print("wrote", sorted(os.listdir(HERE)))
+
+
+def write_display_fixture(data):
+    """Parse the reference's textured test model with THIS repo's loader, write it back as a compact OBJ / MTL / PNG
+    trio and check that loading the copy reproduces the parsed arrays exactly."""
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from neural_renderer_b200 import io
+    src = os.path.join(data, "4e49873292196f02574b5684eaec43e9")
+    out = os.path.join(HERE, "display")
+    os.makedirs(out, exist_ok=True)
+    obj = os.path.join(src, "model.obj")
+    v, f = io.load_obj(obj, normalization=False)
+    uv, names = io.parse_texture_faces(obj)
+    colors, files = io.load_mtl(os.path.join(src, "model.mtl"))
+    png = {}
+    for k, (mat, rel) in enumerate(files.items()):
+        im = Image.open(os.path.join(src, rel)).convert("RGB")
+        png[mat] = "texture%d.png" % k
+        im.save(os.path.join(out, png[mat]))
+    with open(os.path.join(out, "model.mtl"), "w") as fh:
+        for mat, col in colors.items():
+            fh.write("newmtl %s\nKd %.9g %.9g %.9g\n" % (mat, col[0], col[1], col[2]))
+            if mat in png:
+                fh.write("map_Kd %s\n" % png[mat])
+            fh.write("\n")
+    with open(os.path.join(out, "model.obj"), "w") as fh:
+        fh.write("mtllib model.mtl\n")
+        for p in v:
+            fh.write("v %.9g %.9g %.9g\n" % tuple(p))
+        flat = uv.reshape(-1, 2)
+        for t in flat:                      # one vt per face corner (already wrapped; values <= 1 stay as they are)
+            fh.write("vt %.9g %.9g\n" % tuple(t))
+        cur = None
+        for i, face in enumerate(f):
+            if names[i] != cur:
+                cur = names[i]
+                fh.write("usemtl %s\n" % cur)
+            fh.write("f %d/%d %d/%d %d/%d\n" % (face[0] + 1, 3 * i + 1, face[1] + 1, 3 * i + 2, face[2] + 1, 3 * i + 3))
+    v2, f2 = io.load_obj(os.path.join(out, "model.obj"), normalization=False)
+    uv2, names2 = io.parse_texture_faces(os.path.join(out, "model.obj"))
+    c2, files2 = io.load_mtl(os.path.join(out, "model.mtl"))
+    assert np.array_equal(v2, v) and np.array_equal(f2, f) and np.array_equal(uv2, uv) and names2 == names
+    assert list(c2) == list(colors) and all(np.array_equal(c2[k], colors[k]) for k in colors) and list(files2) == list(files)
+    np.savez_compressed(os.path.join(out, "display_u8.npz"), display_u8=np.array(Image.open(os.path.join(data, "display.png"))))
 
 
 if __name__ == "__main__":

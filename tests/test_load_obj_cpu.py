@@ -69,3 +69,25 @@ def test_load_textures_composition_with_oracle(monkeypatch):
     assert np.isnan(tex[1, 0, 0, 0]).all() and np.isfinite(tex[1].reshape(-1, 3)[1:]).all()
     img = io._read_image(os.path.join(os.path.dirname(OBJ), "pattern.png"))[::-1]
     assert np.allclose(tex[1, 3, 0, 0], img[0, 0], atol=1e-6)   # uv (0,0) of the flipped image = bottom-left pixel
+
+
+def test_textured_model_renders_like_the_reference_snapshot(monkeypatch):
+    """The reference's own textured test model (test_load_obj.py:55-62: 3644 faces, 7 materials, 2 texture images,
+    texture_size 16) through THIS loader (OBJ / MTL parsing, image flip, UV wrap, Kd fill, bilinear bake) and the CPU
+    oracle's Renderer, against the display.png the reference's test writes for it.  The snapshot is 8-bit and was
+    min-max scaled by scipy.misc.toimage, so the comparison is on that scale; the model files are the re-serialised
+    copy tests/golden/make_golden.py wrote (tests/golden/display)."""
+    import nr_oracle as o
+    from neural_renderer_b200 import io
+    d = os.path.join(ROOT, "tests", "golden", "display")
+    monkeypatch.setattr(io, "bake_textures", lambda image, uv, upd, ts, tex: o.bake_textures(image, uv, upd, ts, tex))
+    v, f, tex = io.load_obj(os.path.join(d, "model.obj"), load_texture=True, texture_size=16)
+    assert v.shape == (921, 3) and f.shape == (3644, 3) and tex.shape == (3644, 16, 16, 16, 3)
+    r = o.Renderer()
+    r.eye = o.get_points_from_angles(2, 15, -90)
+    img = np.asarray(r.render(v[None], f[None], tex[None])["rgb"])[0].transpose(1, 2, 0)
+    assert np.isfinite(img).all()                      # the NaN texel (0,0,0) of baked cubes is never sampled at ts = 16
+    mine = (img - img.min()) / (img.max() - img.min()) * 255.0
+    ref = np.load(os.path.join(d, "display_u8.npz"))["display_u8"].astype(np.float32)[..., :3]
+    diff = np.abs(mine - ref)
+    assert diff.mean() < 0.5 and diff.max() < 16.0, (diff.mean(), diff.max())   # observed 0.13 / 4.4 grey levels
