@@ -119,3 +119,33 @@ def test_obj_roundtrip(tmp_path, teapot):
     io.save_obj(path, v, f)
     v2, f2 = io.load_obj(path, normalization=False)
     assert np.array_equal(f2, f) and np.allclose(v2, v, atol=1e-6)
+
+
+def test_reference_known_answers_look_at_perspective():
+    """The reference's own known-answer cases: tests/test_look_at.py:12-28 (three eyes) and
+    tests/test_perspective.py:12-18 (default 30 degree viewing angle, pi = 3.1416 as in perspective.py)."""
+    import torch
+    v = torch.tensor([[[1.0, 0.0, 0.0]]])
+    s2 = np.sqrt(2.0)
+    for eye, answer in (([1, 0, 1], [-s2 / 2, 0, s2 / 2]), ([0, 0, -10], [1, 0, 10]), ([-1, 1, 0], [0, s2 / 2, 1.5 * s2])):
+        out = nr.look_at(v, torch.tensor(eye, dtype=torch.float32))
+        np.testing.assert_allclose(out.numpy().ravel(), answer, rtol=1e-4, atol=1e-5)   # chainer.testing default rtol
+        out = nr.look_at(v, eye)                                                        # plain-number eye
+        np.testing.assert_allclose(out.numpy().ravel(), answer, rtol=1e-4, atol=1e-5)
+    out = nr.perspective(torch.tensor([[[1.0, 2.0, 10.0]]]))
+    np.testing.assert_allclose(out.numpy().ravel(), [np.sqrt(3) / 10, 2 * np.sqrt(3) / 10, 10], rtol=1e-4, atol=1e-5)
+
+
+def test_reference_known_answers_load_obj(tmp_path, teapot):
+    """tests/test_load_obj.py:11-37: the tetrahedron (raw and normalised) and the teapot's element counts."""
+    from neural_renderer_b200 import io
+    path = tmp_path / "tetrahedron.obj"
+    path.write_text("v 1 0 0\nv 0 1 0\nv 0 0 1\nv 0 0 0\nf 2 4 3\nf 4 2 1\nf 3 1 2\nf 1 3 4\n")
+    v_ref = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 0, 0]], dtype=np.float32)
+    f_ref = np.array([[1, 3, 2], [3, 1, 0], [2, 0, 1], [0, 2, 3]], dtype=np.int32)
+    v, f = io.load_obj(str(path), False)
+    assert np.allclose(v, v_ref) and np.array_equal(f, f_ref)
+    v, f = io.load_obj(str(path), True)
+    assert np.allclose(v, v_ref * 2 - 1.0) and np.array_equal(f, f_ref)
+    tv, tf = teapot
+    assert tf.shape[0] == 2464 and tv.shape[0] == 1292
