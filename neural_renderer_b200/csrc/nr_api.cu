@@ -21,10 +21,10 @@ std::atomic<bool> g_profiling{false};
 std::mutex g_mu;
 std::deque<Timer> g_timers;  // deque: push_back keeps references to earlier records valid
 thread_local Timer* g_open = nullptr;
-int g_launches = 0;
+std::atomic<int> g_launches{0};  // written by the autograd thread, read by the caller's thread
 }  // namespace
 
-int& launch_count() { return g_launches; }
+std::atomic<int>& launch_count() { return g_launches; }
 
 void prof_begin(const char* name, cudaStream_t stream) {
     g_open = nullptr;
@@ -58,7 +58,7 @@ extern "C" const char* nr_b200_error_string(int code) {
     }
 }
 
-extern "C" int nr_b200_last_launch_count(void) { return nr_internal::launch_count(); }
+extern "C" int nr_b200_last_launch_count(void) { return nr_internal::launch_count().load(); }
 
 extern "C" void nr_b200_set_profiling(int enabled) { nr_internal::g_profiling.store(enabled != 0); }
 

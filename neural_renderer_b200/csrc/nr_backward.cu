@@ -38,6 +38,13 @@
 
 namespace {
 
+// Phase-ablation switches exist only in experiment builds (-DNR_B200_DEBUG_KNOBS); the product never drops a term.
+#ifdef NR_B200_DEBUG_KNOBS
+#define NR_SKIP(p, bit) (((p).debug_skip & (bit)) != 0)
+#else
+#define NR_SKIP(p, bit) false
+#endif
+
 // k_edge_scan<kMode, kT>: kT threads per CTA; 2*kT queued faces (<= 9-bit slot), 8*kT scan tasks (<= 12-bit rank) per round
 constexpr int kEdgeScanThreadsDefault = 128;
 constexpr int kMaxLines = 16;                 // W upper bound (4-bit line in a task word)
@@ -66,7 +73,9 @@ struct BwdParams {
     int W;          // lines per strip (power of two)
     int w_log2, nstrips;
     int len_shift;  // scan length >> len_shift -> one of 32 sort buckets
-    int debug_skip; // ablation knob (NR_B200_ES_SKIP): 1 = no in-scan, 2 = no out-scan, 4 = no task processing at all
+#ifdef NR_B200_DEBUG_KNOBS
+    int debug_skip; // ablation knob of experiment builds (NR_B200_ES_SKIP): 1 = no in-scan, 2 = no out-scan, 4 = no task processing
+#endif
     uint32_t flags;
     float eps, two_over_S, tex_cmp, tex_val;
 };
@@ -273,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
         Px q;
         q.c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         q.A = q.g0 = q.g1 = q.g2 = q.ga = 0.f;
-        if (d1 >= S || (p.debug_skip & 8)) return q;  // the padding pixel of an odd raster size stays zero
+        if (d1 >= S || NR_SKIP(p, 8)) return q;  // the padding pixel of an odd raster size stays zero
         const int x = (axis == 0) ? l0 + line : d1, y = (axis == 0) ? d1 : l0 + line;
         const int row = S - 1 - y;
         const size_t o = (size_t)row * S + x;
@@ -409,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
     const int* own = p.strip_list + __ldg(p.strip_off + cid + blockIdx.x);
     const int* wide = p.strip_list + __ldg(p.strip_off + cid + p.nstrips);
     const int ncand = n_own + n_wide;
-    for (int base = 0; base < ncand && !(p.debug_skip & 16); base += kThreads) {
+    for (int base = 0; base < ncand && !NR_SKIP(p, 16); base += kThreads) {
         // ---- 2a. this strip's faces (binned by k_strip_bin) plus the item's wide faces that overlap it
         const int i = base + tid;
         const bool last = base + kThreads >= ncand;
@@ -491,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                 int t0 = 0;
                 if (lane == 0) t0 = atomicAdd(&s_next, 32);
                 t0 = __shfl_sync(0xffffffffu, t0, 0);
-                if (t0 >= ntask || (p.debug_skip & 4)) break;
+                if (t0 >= ntask || NR_SKIP(p, 4)) break;
                 const int t = t0 + lane;
                 Task T;
                 T.valid = false; T.out_from = 0; T.out_to = -1; T.in_from = 0; T.in_to = -1;
@@ -511,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                     {   // in-scan (rasterize.py:662-730): reference colour = outside pixel, only pixels that show this face
                         const float4 cout = lci[T.d1_out];
                         const float ra = (kMode == 3) ? ((__float_as_int(cout.w) >= 0) ? 1.0f : 0.0f) : 0.0f;
-                        for (int d1 = T.in_from; d1 <= T.in_to && !(p.debug_skip & 1); d1++) {
+                        for (int d1 = T.in_from; d1 <= T.in_to && !NR_SKIP(p, 1); d1++) {
                             if (__float_as_int(lci[d1].w) != fn) continue;
                             visit(T, line, d1, cout.x, cout.y, cout.z, ra, acc0, acc1);
                         }
@@ -528,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                 // along an out-scan (d1 - d1_cross) keeps the sign of dir, so the sign of eps is fixed per vertex
                 const float fdir = (float)T.dir;
                 const float e0 = (fdir * T.k0 > 0.0f) ? p.eps : -p.eps, e1 = (fdir * T.k1 > 0.0f) ? p.eps : -p.eps;
-                const int my_from = (fast && !(p.debug_skip & 2)) ? T.out_from : 1, my_to = (fast && !(p.debug_skip & 2)) ? T.out_to : 0;
+                const int my_from = (fast && !NR_SKIP(p, 2)) ? T.out_from : 1, my_to = (fast && !NR_SKIP(p, 2)) ? T.out_to : 0;
                 float* gfb = p.grad_faces + ((size_t)b * p.F + fn) * 9 + (1 - axis);
                 const int qd = lane >> 2, j = lane & 3;  // 8 tasks per pass, 4 lanes (8 pixels per step) each
 #pragma unroll 1
@@ -788,8 +797,8 @@ inline float float_le(double d) {
 
 template <int kMode, int kT>
 int launch_edge_scan_t(const BwdParams& p, int nstrips, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(k_edge_scan<kMode, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return NR_ERR_CUDA;
+    static nr_internal::SmemOptIn optin;
+    if (optin.ensure(k_edge_scan<kMode, kT>, smem) != cudaSuccess) return NR_ERR_CUDA;
     nr_internal::LaunchScope ls("k_edge_scan", stream);
     k_edge_scan<kMode, kT><<<dim3(nstrips, 2, p.B), kT, smem, stream>>>(p);
     return NR_OK;
@@ -798,7 +807,9 @@ int launch_edge_scan_t(const BwdParams& p, int nstrips, size_t smem, cudaStream_
 template <int kMode>
 int launch_edge_scan(const BwdParams& p, int nstrips, size_t smem, cudaStream_t stream) {
     int threads = kEdgeScanThreadsDefault;
-    if (const char* env = getenv("NR_B200_ES_THREADS")) threads = atoi(env);  // tuning knob
+#ifdef NR_B200_TUNING
+    if (const char* env = getenv("NR_B200_ES_THREADS")) threads = atoi(env);
+#endif
     if (threads == 256) return launch_edge_scan_t<kMode, 256>(p, nstrips, smem, stream);
     return launch_edge_scan_t<kMode, 128>(p, nstrips, smem, stream);
 }
@@ -814,13 +825,16 @@ struct BinLayout {
 BinLayout bin_layout(int B, int F, int S, int rec_bytes) {
     BinLayout L{};
     size_t strip_bytes = kStripBytesDefault;
-    if (const char* env = getenv("NR_B200_STRIP_KB")) strip_bytes = (size_t)atoi(env) * 1024;  // tuning knob
+    bool strip_forced = false;
+#ifdef NR_B200_TUNING
+    if (const char* env = getenv("NR_B200_STRIP_KB")) { strip_bytes = (size_t)atoi(env) * 1024; strip_forced = true; }
+#endif
     int W = kMaxLines;
     while (W > 1 && (size_t)W * ((S + 1) & ~1) * rec_bytes > strip_bytes) W >>= 1;
     // one-line strips pay the per-CTA front end (staging, face list, task sort) per line: two lines are worth twice
     // the shared memory up to 32 KB (raster 512: 3.5 -> 3.3 ms at the Renderer-default shape, 4.3 -> 3.2 ms at 70 k
     // faces); beyond that the lost occupancy costs more (measured with 64 KB)
-    if (W == 1 && !getenv("NR_B200_STRIP_KB") && (size_t)2 * ((S + 1) & ~1) * rec_bytes <= 2 * (size_t)kStripBytesDefault) W = 2;
+    if (W == 1 && !strip_forced && (size_t)2 * ((S + 1) & ~1) * rec_bytes <= 2 * (size_t)kStripBytesDefault) W = 2;
     L.W = W;
     L.w_log2 = 0;
     while ((1 << L.w_log2) < W) L.w_log2++;
@@ -901,7 +915,9 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
         const int W = L.W;
         p.W = W; p.w_log2 = L.w_log2; p.nstrips = L.nstrips;
         p.len_shift = 3;
+#ifdef NR_B200_DEBUG_KNOBS
         p.debug_skip = getenv("NR_B200_ES_SKIP") ? atoi(getenv("NR_B200_ES_SKIP")) : 0;
+#endif
         while ((2 * S) >> p.len_shift > 32) p.len_shift++;
         const size_t smem = (size_t)W * ((S + 1) & ~1) * rec_bytes;
         if (smem > 160 * 1024) return NR_ERR_UNSUPPORTED;
@@ -914,7 +930,10 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
         if (cudaMemsetAsync(cnt, 0, L.off_list - L.off_cnt, stream) != cudaSuccess) return NR_ERR_CUDA;  // counters, offsets, cursors
         {
             const dim3 g((F + 255) / 256, B);
-            const bool bin_smem = nstrips + 1 <= kBinSmemStrips && !getenv("NR_B200_BIN_GLOBAL");
+            bool bin_smem = nstrips + 1 <= kBinSmemStrips;
+#ifdef NR_B200_TUNING
+            if (getenv("NR_B200_BIN_GLOBAL")) bin_smem = false;
+#endif
             const size_t bin_bytes = (size_t)4 * (nstrips + 1) * sizeof(int);
             {
                 nr_internal::LaunchScope ls("k_strip_bin", stream);

@@ -512,16 +512,18 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
     p.fim = a->face_index_map; p.wmap = a->weight_map; p.dmap = a->depth_map; p.rgb = a->rgb_map; p.alpha = a->alpha_map;
     p.out_rgb = a->out_rgb; p.out_alpha = a->out_alpha; p.out_depth = a->out_depth;
     p.B = B; p.F = F; p.S = S; p.ts = ts; p.ngroups = ngroups;
-    int tl = kFwdTileLog2Default, threads = kFwdThreadsDefault;  // tuning knobs: NR_B200_FWD_TILE (5|6), NR_B200_FWD_THREADS (128|256)
-    if (const char* env = getenv("NR_B200_FWD_TILE")) tl = atoi(env) <= 5 ? 5 : 6;  // 65 = 64 wide x 32 tall
+    int tl = kFwdTileLog2Default, threads = kFwdThreadsDefault;
+    bool force_square = false;
+#ifdef NR_B200_TUNING  // experiment builds only: NR_B200_FWD_TILE (5|6), NR_B200_FWD_THREADS (128|256)
+    if (const char* env = getenv("NR_B200_FWD_TILE")) { tl = atoi(env) <= 5 ? 5 : 6; force_square = atoi(env) == 6; }
     if (const char* env = getenv("NR_B200_FWD_THREADS")) threads = atoi(env) == 128 ? 128 : 256;
+#endif
     // shrink the tile for small rasters so that it is not mostly padding (the kernels are compiled for 32 / 64 pixel
     // tiles; smaller rasters run the 32-pixel variant with the tile clipped to the image)
     while (tl > 3 && (1 << (tl - 1)) >= S) tl--;
-    const int tile_log2 = tl;
-    tl = tile_log2 >= 6 ? 6 : 5;
-    // default: 64 wide x 32 tall tiles (4 CTAs of 256 threads per SM); NR_B200_FWD_TILE=6 forces 64 x 64, 5 -> 32 x 32
-    const bool wide = (tl == 6) && !(getenv("NR_B200_FWD_TILE") && atoi(getenv("NR_B200_FWD_TILE")) == 6);
+    tl = tl >= 6 ? 6 : 5;
+    // default: 64 wide x 32 tall tiles (4 CTAs of 256 threads per SM)
+    const bool wide = (tl == 6) && !force_square;
     p.tw_log2 = tl; p.th_log2 = wide ? 5 : tl;
     p.tiles_x = (S + (1 << tl) - 1) >> tl;
     const int tiles_y = (S + (1 << p.th_log2) - 1) >> p.th_log2;
@@ -540,7 +542,8 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
 #define NR_LAUNCH_TILE(AA, TL2, T)                                                                                         \
     do {                                                                                                                   \
         const size_t smem = sizeof(TileShared<TL2, T>);                                                                    \
-        e = cudaFuncSetAttribute(k_raster_tile<AA, TL2, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+        static nr_internal::SmemOptIn optin;                                                                               \
+        e = optin.ensure(k_raster_tile<AA, TL2, T>, smem);                                                                 \
         if (e != cudaSuccess) return NR_ERR_CUDA;                                                                          \
         nr_internal::LaunchScope ls("k_raster_tile", stream);                                                              \
         k_raster_tile<AA, TL2, T><<<grid, T, smem, stream>>>(p);                                                           \

@@ -2,9 +2,11 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 namespace nr_internal {
 // kernels launched by the last forward/backward call on this thread (nr_b200_last_launch_count)
-int& launch_count();
+std::atomic<int>& launch_count();
 // optional per-kernel CUDA-event timing on the launching stream (nr_b200_set_profiling / nr_b200_read_profile)
 void prof_begin(const char* name, cudaStream_t stream);
 void prof_end(cudaStream_t stream);
@@ -13,5 +15,24 @@ struct LaunchScope {
     cudaStream_t s;
     LaunchScope(const char* name, cudaStream_t stream) : s(stream) { prof_begin(name, s); }
     ~LaunchScope() { prof_end(s); launch_count()++; }
+};
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is issued once per (kernel instantiation, device, size high-water
+// mark) instead of on every launch: `slot` is a function-local static of the launching template.
+struct SmemOptIn {
+    static constexpr int kMaxDevices = 64;
+    std::atomic<int> bytes[kMaxDevices];
+    SmemOptIn() { for (auto& b : bytes) b.store(0, std::memory_order_relaxed); }
+    template <typename Kernel>
+    cudaError_t ensure(Kernel kernel, size_t need) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= kMaxDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+        if ((int)need <= bytes[dev].load(std::memory_order_acquire)) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+        if (e == cudaSuccess) bytes[dev].store((int)need, std::memory_order_release);
+        return e;
+    }
 };
 }  // namespace nr_internal

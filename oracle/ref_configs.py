@@ -37,4 +37,6 @@ def all_configs():
     c.append(cfg(256, 5000, 0, NEAR, FAR, 1e-4, 0, 0, 1))
     # config 3 of BASELINE.json (bunny-scale): ~70k faces, depth + RGB, 512x512
     c.append(cfg(512, 70000, 2, NEAR, FAR, 1e-4, 1, 0, 1))
+    # config 5 of BASELINE.json at reduced size: one shared 100k-face mesh, 512x512, RGB through Renderer.render (eps 1e-3)
+    c.append(cfg(512, 100000, 2, NEAR, FAR, 1e-3, 1, 0, 0))
     return c
