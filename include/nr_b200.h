@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define NR_B200_ABI_VERSION 2
+#define NR_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define NR_B200_API __attribute__((visibility("default")))
@@ -65,6 +65,18 @@ extern "C" {
                                 /* [0, F/2); `textures` / `grad_textures` hold F/2 cubes and face f >= F/2 samples */
                                 /* cube f - F/2 with its three texture axes reversed (permute(0,1,4,3,2,5))        */
 
+/* ABI 3 */
+#define NR_FACES_INDEXED 0x800u   /* geometry is `vertices` [B,Nv,3] + `face_indices` (vertices_to_faces.py:16-21 folded   */
+                                  /* into the rasterizer): `faces` is ignored, no [B,F,3,3] tensor exists on either pass;   */
+                                  /* the backward scatters d loss / d vertex straight into `grad_vertices`                  */
+#define NR_INDICES_SHARED 0x1000u /* face_indices is [F,3] and serves every batch item (else [B,F,3])                       */
+#define NR_TEX_SHARED 0x2000u     /* ONE set of texture cubes [F,ts,ts,ts,3] serves every batch item (a shared mesh seen   */
+                                  /* from B viewpoints, mesh.py:29-34); grad_textures [F,...] is the sum over the items     */
+#define NR_BWD_PART_TEXTURES 0x4000u /* backward: only the part that produces grad_textures / grad_face_light (K6)         */
+#define NR_BWD_PART_FACES 0x8000u    /* backward: only the part that produces grad_faces / grad_vertices (K5, K7)           */
+                                     /* neither bit = both parts; a caller that wants to start a collective on the texture   */
+                                     /* gradient while the edge scan runs calls TEXTURES first, then FACES                   */
+
 typedef struct nr_b200_forward_args {
     uint32_t struct_size; /* sizeof(nr_b200_forward_args), for ABI evolution */
     uint32_t flags;
@@ -78,7 +90,7 @@ typedef struct nr_b200_forward_args {
     float background[3];  /* uniform background colour (host values)                                             */
     float _pad0;
     const float *faces;            /* [B,F,3,3]  x,y in NDC [-1,1], z = camera depth                            */
-    const float *textures;         /* [B,F,ts,ts,ts,3] or NULL                                                  */
+    const float *textures;         /* [B,F,ts,ts,ts,3] ([F,...] with NR_TEX_SHARED) or NULL                     */
     const float *background_batch; /* [B,3] device, only with NR_BG_PER_BATCH                                   */
     /* raster-resolution maps, saved for the backward pass (all required unless noted) */
     int32_t *face_index_map; /* [B,S,S]   -1 where empty                                                      */
@@ -97,6 +109,12 @@ typedef struct nr_b200_forward_args {
      * face_light[b,f,:] before the trilinear blend, bit-identical to sampling the materialised `textures * light`
      * product (lighting.py:52).  NULL = unlit. */
     const float *face_light; /* [B,F,3] or NULL */
+    /* ABI 3: indexed geometry, only with NR_FACES_INDEXED (then `faces` may be NULL).  Indices outside [0, Nv) read
+     * a vertex of zeros, like nr_b200_vertices_to_faces. */
+    const float *vertices;       /* [B,Nv,3] x,y in NDC, z = camera depth */
+    const int32_t *face_indices; /* [B,F,3], or [F,3] with NR_INDICES_SHARED */
+    int32_t num_vertices;        /* Nv */
+    int32_t _pad1;
 } nr_b200_forward_args;
 
 typedef struct nr_b200_backward_args {
@@ -115,7 +133,7 @@ typedef struct nr_b200_backward_args {
     const float *grad_alpha; /* [B,H,W]   */
     const float *grad_depth; /* [B,H,W]   */
     float *grad_faces;    /* [B,F,3,3]                 */
-    float *grad_textures; /* [B,F,ts,ts,ts,3] ([B,F/2,...] with NR_TEX_FILL_BACK) or NULL  */
+    float *grad_textures; /* [B,F,ts,ts,ts,3] ([B,F/2,...] with NR_TEX_FILL_BACK, no B with NR_TEX_SHARED) or NULL */
     void *workspace;
     size_t workspace_bytes;
     /* ABI 2: lighting folded into the sampler.  grad_textures receives the gradient of the UNLIT textures
@@ -123,6 +141,13 @@ typedef struct nr_b200_backward_args {
      * grad_rgb * unlit sample and needs `textures`. */
     const float *face_light; /* [B,F,3] as given to the forward call, or NULL */
     float *grad_face_light;  /* [B,F,3] or NULL */
+    /* ABI 3: indexed geometry as in the forward call; with NR_FACES_INDEXED the face gradient is reduced into
+     * grad_vertices [B,Nv,3] (zero-filled first unless NR_GRAD_ACCUMULATE) and grad_faces may be NULL. */
+    const float *vertices;
+    const int32_t *face_indices;
+    float *grad_vertices; /* [B,Nv,3] */
+    int32_t num_vertices;
+    int32_t _pad1;
 } nr_b200_backward_args;
 
 /* ABI version of the loaded library (== NR_B200_ABI_VERSION it was built with). */
@@ -168,6 +193,7 @@ NR_B200_API int nr_b200_camera_transform_backward(const float *vertices, const f
 /* Per-face light factor of lighting.py:29-51, straight from vertices and face indices:
  *   n = normalize(cross(v0 - v1, v2 - v1))  (x / (|x| + 1e-5), like chainer.functions.normalize)
  *   face_light[b,f,:] = ambient + directional * max(n . direction, 0)
+ * `faces` is [B,Nf,3] int32, or [Nf,3] with NR_INDICES_SHARED (ABI 3).
  * light_params [B,9] (or [1,9] with NR_CAM_SHARED) = {intensity_ambient * color_ambient (3),
  * intensity_directional * color_directional (3), direction (3)}, device memory.  The factor is consumed by
  * nr_b200_forward_args.face_light; the backward turns d loss / d face_light (nr_b200_backward_args.grad_face_light)

@@ -22,8 +22,13 @@ NR_GRAD_ACCUMULATE = 64
 NR_CAM_PERSPECTIVE = 0x100
 NR_TEX_FILL_BACK = 0x400
 NR_CAM_SHARED = 0x200
+NR_FACES_INDEXED = 0x800
+NR_INDICES_SHARED = 0x1000
+NR_TEX_SHARED = 0x2000
+NR_BWD_PART_TEXTURES = 0x4000
+NR_BWD_PART_FACES = 0x8000
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/nr_b200.h declares
 EXPORTED_SYMBOLS = (
@@ -59,6 +64,8 @@ class ForwardArgs(ctypes.Structure):
         ("out_rgb", ctypes.c_void_p), ("out_alpha", ctypes.c_void_p), ("out_depth", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("face_light", ctypes.c_void_p),
+        ("vertices", ctypes.c_void_p), ("face_indices", ctypes.c_void_p),
+        ("num_vertices", ctypes.c_int32), ("_pad1", ctypes.c_int32),
     ]
 
 
@@ -75,6 +82,8 @@ class BackwardArgs(ctypes.Structure):
         ("grad_faces", ctypes.c_void_p), ("grad_textures", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("face_light", ctypes.c_void_p), ("grad_face_light", ctypes.c_void_p),
+        ("vertices", ctypes.c_void_p), ("face_indices", ctypes.c_void_p), ("grad_vertices", ctypes.c_void_p),
+        ("num_vertices", ctypes.c_int32), ("_pad1", ctypes.c_int32),
     ]
 
 

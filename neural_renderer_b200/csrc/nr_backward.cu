@@ -51,7 +51,9 @@ constexpr int kMaxLines = 16;                 // W upper bound (4-bit line in a 
 constexpr int kStripBytesDefault = 16 * 1024; // shared memory budget for the staged strip (NR_B200_STRIP_KB overrides)
 
 struct BwdParams {
-    const float* faces;
+    nr::FaceSrc src;
+    nr::FaceGrad dst;
+    size_t tex_bstride;  // cubes per batch item in textures / grad_textures (0 with NR_TEX_SHARED)
     const int32_t* fim;
     const float* wmap;
     const float* dmap;
@@ -64,7 +66,6 @@ struct BwdParams {
     const int* strip_cnt;   // [B*2*(nstrips+1)]  faces per (item, axis, strip); slot nstrips = faces wider than kWideStrips
     const int* strip_off;   // exclusive prefix of strip_cnt
     const int* strip_list;  // face indices, grouped by (item, axis, strip)
-    float* grad_faces;
     float* grad_textures;
     const float* textures;
     const float* face_light;
@@ -340,19 +341,19 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
         bool valid;
     };
     auto task_setup = [&](int f, int e, int line, Task& T) {
-        const float* v = p.faces + ((size_t)b * p.F + f) * 9;
         const int pi0 = e, pi1 = (e + 1) % 3, pi2 = (e + 2) % 3;
+        const float *v0 = nr::face_vertex(p.src, b, f, pi0), *v1 = nr::face_vertex(p.src, b, f, pi1);
         const int a = axis, c = 1 - axis;
         T.pi0 = pi0; T.pi1 = pi1;
         T.valid = false;
         T.out_from = 0; T.out_to = -1; T.in_from = 0; T.in_to = -1;
-        const float p00 = nr::to_pixel(__ldg(v + 3 * pi0 + a), fS), p10 = nr::to_pixel(__ldg(v + 3 * pi1 + a), fS);
+        const float p00 = nr::to_pixel(__ldg(v0 + a), fS), p10 = nr::to_pixel(__ldg(v1 + a), fS);
         // (int)max(ceil(min(p0,p1)), 0.) and (int)min(max(p0,p1), is - 1.): truncating conversions (NaN -> 0)
         const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p00, p10)), 0.0f));
         const int d0_to = __float2int_rz(fminf(fmaxf(p00, p10), (float)(S - 1)));
         const int d0 = l0 + line;
         if (d0 < d0_from || d0 > d0_to) return;  // most (face, edge, line) slots end here
-        const float p01 = nr::to_pixel(__ldg(v + 3 * pi0 + c), fS), p11 = nr::to_pixel(__ldg(v + 3 * pi1 + c), fS);
+        const float p01 = nr::to_pixel(__ldg(v0 + c), fS), p11 = nr::to_pixel(__ldg(v1 + c), fS);
         const bool lt = p00 < p10;
         T.dir = (axis == 0) ? (lt ? -1 : 1) : (lt ? 1 : -1);
         const float fd0 = (float)d0;
@@ -373,7 +374,8 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
             T.out_to = min(max(T.d1_out, lim), S - 1);
         }
         // in-scan: from the inside pixel to where this line leaves the face through one of the other two edges
-        const float p20 = nr::to_pixel(__ldg(v + 3 * pi2 + a), fS), p21 = nr::to_pixel(__ldg(v + 3 * pi2 + c), fS);
+        const float* v2 = nr::face_vertex(p.src, b, f, pi2);
+        const float p20 = nr::to_pixel(__ldg(v2 + a), fS), p21 = nr::to_pixel(__ldg(v2 + c), fS);
         float ba, bb, ea, eb;
         if (__fmul_rn(__fsub_rn(fd0, p00), __fsub_rn(fd0, p20)) < 0.0f) { ba = p00; bb = p01; ea = p20; eb = p21; }
         else { ba = p20; bb = p21; ea = p10; eb = p11; }
@@ -456,8 +458,8 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                 const int e = i % 3, q = q0 + i / 3;
                 const int f = s_faceq[q];
                 // lines of the strip that this edge spans (same truncating conversions as task_setup)
-                const float* v = p.faces + ((size_t)b * p.F + f) * 9;
-                const float p00 = nr::to_pixel(__ldg(v + 3 * e + axis), fS), p10 = nr::to_pixel(__ldg(v + 3 * ((e + 1) % 3) + axis), fS);
+                const float p00 = nr::to_pixel(__ldg(nr::face_vertex(p.src, b, f, e) + axis), fS),
+                            p10 = nr::to_pixel(__ldg(nr::face_vertex(p.src, b, f, (e + 1) % 3) + axis), fS);
                 const int lo = max(__float2int_rz(fmaxf(ceilf(fminf(p00, p10)), 0.0f)), l0);
                 const int hi = min(__float2int_rz(fminf(fmaxf(p00, p10), (float)(S - 1))), lhi);
                 for (int d0 = lo; d0 <= hi; d0++) {
@@ -538,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                 const float fdir = (float)T.dir;
                 const float e0 = (fdir * T.k0 > 0.0f) ? p.eps : -p.eps, e1 = (fdir * T.k1 > 0.0f) ? p.eps : -p.eps;
                 const int my_from = (fast && !NR_SKIP(p, 2)) ? T.out_from : 1, my_to = (fast && !NR_SKIP(p, 2)) ? T.out_to : 0;
-                float* gfb = p.grad_faces + ((size_t)b * p.F + fn) * 9 + (1 - axis);
+
                 const int qd = lane >> 2, j = lane & 3;  // 8 tasks per pass, 4 lanes (8 pixels per step) each
 #pragma unroll 1
                 for (int sub = 0; sub < 4; sub++) {
@@ -626,8 +628,8 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                     const float r0 = __shfl_sync(0xffffffffu, s0, (lane & 7) << 2), r1 = __shfl_sync(0xffffffffu, s1, (lane & 7) << 2);
                     if ((lane >> 3) == sub) { acc0 -= r0; acc1 -= r1; }
                 }
-                if (acc0 != 0.0f) atomicAdd(gfb + 3 * T.pi0, acc0);
-                if (acc1 != 0.0f) atomicAdd(gfb + 3 * T.pi1, acc1);
+                if (acc0 != 0.0f) { float* g = nr::face_grad_vertex(p.dst, b, fn, T.pi0); if (g) atomicAdd(g + (1 - axis), acc0); }
+                if (acc1 != 0.0f) { float* g = nr::face_grad_vertex(p.dst, b, fn, T.pi1); if (g) atomicAdd(g + (1 - axis), acc1); }
             }
             __syncthreads();
             if (tid < 32) s_hist[tid] = 0;
@@ -659,9 +661,11 @@ __global__ void __launch_bounds__(256) k_texture_grad(const __grid_constant__ Bw
         const float* wm = p.wmap + (size_t)b * 3 * plane + i;
         const float w[3] = {__ldg(wm), __ldg(wm + plane), __ldg(wm + 2 * plane)};
         const float zp = __ldg(p.dmap + (size_t)b * plane + i);
-        const float* v = p.faces + ((size_t)((p.flags & NR_TEX_Z_BATCH0) ? 0 : b) * p.F + fn) * 9;
+        const int zb = (p.flags & NR_TEX_Z_BATCH0) ? 0 : b;
         const int ts = p.ts;
-        const nr::TexCoord tc = nr::texture_coords(w, zp, __ldg(v + 2), __ldg(v + 5), __ldg(v + 8), ts, p.tex_cmp, p.tex_val);
+        const nr::TexCoord tc = nr::texture_coords(w, zp, __ldg(nr::face_vertex(p.src, zb, fn, 0) + 2),
+                                                   __ldg(nr::face_vertex(p.src, zb, fn, 1) + 2),
+                                                   __ldg(nr::face_vertex(p.src, zb, fn, 2) + 2), ts, p.tex_cmp, p.tex_val);
         // NR_TEX_FILL_BACK: the reversed copy of face f - F/2 shares that face's cube, axes reversed
         int cube = fn, ncubes = p.F;
         bool rev = false;
@@ -669,7 +673,7 @@ __global__ void __launch_bounds__(256) k_texture_grad(const __grid_constant__ Bw
             ncubes = p.F >> 1;
             if (fn >= ncubes) { cube = fn - ncubes; rev = true; }
         }
-        const size_t cube_off = ((size_t)b * ncubes + cube) * (size_t)(ts * ts * ts) * 3;
+        const size_t cube_off = ((size_t)b * p.tex_bstride + cube) * (size_t)(ts * ts * ts) * 3;
         if (want_light) {  // unlit sample (same blend as the forward pass) times the upstream gradient
             const float* tex = p.textures + cube_off;
             float r = 0.0f, g = 0.0f, bl = 0.0f;
@@ -740,10 +744,8 @@ __global__ void __launch_bounds__(256) k_depth_grad(const __grid_constant__ BwdP
         const int row = (int)(i / S), col = (int)(i % S);
         const bool aa = (p.flags & NR_ANTI_ALIASING) != 0;
         const float g = load_grad(p.g_depth, aa, S, (size_t)b, row, col);
-        const float* v = p.faces + ((size_t)b * p.F + fn) * 9;
         float c[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) c[k] = __ldg(v + k);
+        nr::load_face(p.src, b, fn, c);
         const float fS = (float)S;
         float inv[9];
         nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS), nr::to_pixel(c[4], fS),
@@ -783,9 +785,11 @@ __global__ void __launch_bounds__(256) k_depth_grad(const __grid_constant__ BwdP
         }
     }
     if (fn >= 0 && ((heads >> lane) & 1u)) {
-        float* gf = p.grad_faces + ((size_t)b * p.F + fn) * 9;
 #pragma unroll
-        for (int k = 0; k < 9; k++) atomicAdd(gf + k, out[k]);
+        for (int k = 0; k < 3; k++) {
+            float* gf = nr::face_grad_vertex(p.dst, b, fn, k);
+            if (gf) { atomicAdd(gf, out[3 * k]); atomicAdd(gf + 1, out[3 * k + 1]); atomicAdd(gf + 2, out[3 * k + 2]); }
+        }
     }
 }
 
@@ -862,9 +866,19 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
     const int B = a->batch_size, F = a->num_faces, S = a->raster_size, ts = a->texture_size;
     const uint32_t flags = a->flags;
     if (B <= 0 || F <= 0 || S <= 0) return NR_ERR_INVALID_ARG;
-    if (!a->faces || !a->face_index_map || !a->weight_map || !a->depth_map || !a->grad_faces) return NR_ERR_INVALID_ARG;
+    if (!a->face_index_map || !a->weight_map || !a->depth_map) return NR_ERR_INVALID_ARG;
+    // the two halves of the pass can be issued separately (NR_BWD_PART_*): textures first lets the caller start a
+    // collective on grad_textures while the edge scan runs
+    const bool part_tex = !(flags & NR_BWD_PART_FACES) || (flags & NR_BWD_PART_TEXTURES);
+    const bool part_faces = !(flags & NR_BWD_PART_TEXTURES) || (flags & NR_BWD_PART_FACES);
+    nr::FaceSrc src{};
+    nr::FaceGrad dst{};
+    if (!nr_internal::make_face_src(flags, a->faces, a->vertices, a->face_indices, F, a->num_vertices, &src)) return NR_ERR_INVALID_ARG;
+    if (part_faces && !nr_internal::make_face_grad(flags, a->grad_faces, a->grad_vertices, a->face_indices, F, a->num_vertices, &dst))
+        return NR_ERR_INVALID_ARG;
     const bool rgb = (flags & NR_RETURN_RGB) != 0, alpha = (flags & NR_RETURN_ALPHA) != 0, depth = (flags & NR_RETURN_DEPTH) != 0;
-    if (rgb && (!a->rgb_map || !a->grad_textures || ts < 2)) return NR_ERR_INVALID_ARG;
+    if (rgb && (!a->rgb_map || ts < 2)) return NR_ERR_INVALID_ARG;
+    if (rgb && part_tex && !a->grad_textures) return NR_ERR_INVALID_ARG;
     if (rgb && (flags & NR_TEX_FILL_BACK) && (F & 1)) return NR_ERR_INVALID_ARG;
     if (rgb && a->grad_face_light && !a->textures) return NR_ERR_INVALID_ARG;
     if ((flags & NR_ANTI_ALIASING) && (S & 1)) return NR_ERR_INVALID_ARG;
@@ -874,21 +888,29 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
     if (!a->workspace || a->workspace_bytes < need || ((uintptr_t)a->workspace & 15)) return NR_ERR_WORKSPACE;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
 
+    const size_t ncubes = (flags & NR_TEX_FILL_BACK) ? (size_t)F / 2 : (size_t)F;
+    const size_t tex_items = (flags & NR_TEX_SHARED) ? 1 : (size_t)B;
     if (!(flags & NR_GRAD_ACCUMULATE)) {
         nr_internal::prof_begin("memset_grads", stream);
-        if (cudaMemsetAsync(a->grad_faces, 0, (size_t)B * F * 9 * sizeof(float), stream) != cudaSuccess) return NR_ERR_CUDA;
-        const size_t ncubes = (flags & NR_TEX_FILL_BACK) ? (size_t)F / 2 : (size_t)F;
-        if (rgb && cudaMemsetAsync(a->grad_textures, 0, (size_t)B * ncubes * ts * ts * ts * 3 * sizeof(float), stream) != cudaSuccess)
+        if (part_faces) {
+            const cudaError_t e = (flags & NR_FACES_INDEXED)
+                ? cudaMemsetAsync(a->grad_vertices, 0, (size_t)B * a->num_vertices * 3 * sizeof(float), stream)
+                : cudaMemsetAsync(a->grad_faces, 0, (size_t)B * F * 9 * sizeof(float), stream);
+            if (e != cudaSuccess) return NR_ERR_CUDA;
+        }
+        if (part_tex && rgb && cudaMemsetAsync(a->grad_textures, 0, tex_items * ncubes * ts * ts * ts * 3 * sizeof(float), stream) != cudaSuccess)
             return NR_ERR_CUDA;
-        if (rgb && a->grad_face_light && cudaMemsetAsync(a->grad_face_light, 0, (size_t)B * F * 3 * sizeof(float), stream) != cudaSuccess)
+        if (part_tex && rgb && a->grad_face_light && cudaMemsetAsync(a->grad_face_light, 0, (size_t)B * F * 3 * sizeof(float), stream) != cudaSuccess)
             return NR_ERR_CUDA;
         nr_internal::prof_end(stream);
     }
 
     BwdParams p{};
-    p.faces = a->faces; p.fim = a->face_index_map; p.wmap = a->weight_map; p.dmap = a->depth_map; p.rgb = a->rgb_map;
+    p.src = src; p.dst = dst;
+    p.tex_bstride = (flags & NR_TEX_SHARED) ? 0 : ncubes;
+    p.fim = a->face_index_map; p.wmap = a->weight_map; p.dmap = a->depth_map; p.rgb = a->rgb_map;
     p.g_rgb = rgb ? a->grad_rgb : nullptr; p.g_alpha = alpha ? a->grad_alpha : nullptr; p.g_depth = depth ? a->grad_depth : nullptr;
-    p.grad_faces = a->grad_faces; p.grad_textures = a->grad_textures;
+    p.grad_textures = a->grad_textures;
     p.textures = a->textures; p.face_light = rgb ? a->face_light : nullptr; p.grad_face_light = rgb ? a->grad_face_light : nullptr;
     p.B = B; p.F = F; p.S = S; p.ts = ts;
     p.flags = flags;
@@ -898,6 +920,13 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
     p.tex_cmp = float_le(tmax);
     p.tex_val = (float)tmax;
 
+    const dim3 pgrid((unsigned)(((size_t)S * S + 255) / 256), B);
+    if (part_tex && rgb && p.g_rgb) {
+        nr_internal::LaunchScope ls("k_texture_grad", stream);
+        k_texture_grad<<<pgrid, 256, 0, stream>>>(p);
+    }
+    if (!part_faces) return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
+
     // K5 runs when an rgb or alpha gradient exists (rasterize.py:523); without upstream gradients it contributes 0
     const bool need_scan = (rgb && p.g_rgb) || (alpha && p.g_alpha);
     if (need_scan) {
@@ -906,7 +935,7 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
         uint2* cbox = (uint2*)((char*)a->workspace + nr_align_up((size_t)B * F * sizeof(uint2), 256));
         {
             nr_internal::LaunchScope ls("k_face_bbox", stream);
-            k_face_bbox<<<dim3(nchunks, B), kChunk, 0, stream>>>(a->faces, F, S, ngroups, bbox, cbox);
+            k_face_bbox<<<dim3(nchunks, B), kChunk, 0, stream>>>(src, F, S, ngroups, bbox, cbox);
         }
         p.bbox = bbox; p.chunk_bbox = cbox; p.nchunks = ngroups;
         const bool use_rgb = rgb && p.g_rgb, use_alpha = alpha && p.g_alpha;
@@ -956,11 +985,6 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
         else if (use_rgb) rc = launch_edge_scan<1>(p, nstrips, smem, stream);
         else rc = launch_edge_scan<2>(p, nstrips, smem, stream);
         if (rc != NR_OK) return rc;
-    }
-    const dim3 pgrid((unsigned)(((size_t)S * S + 255) / 256), B);
-    if (rgb && p.g_rgb) {
-        nr_internal::LaunchScope ls("k_texture_grad", stream);
-        k_texture_grad<<<pgrid, 256, 0, stream>>>(p);
     }
     if (depth && p.g_depth) {
         nr_internal::LaunchScope ls("k_depth_grad", stream);

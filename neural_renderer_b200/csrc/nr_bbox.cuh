@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "nr_geom.cuh"
 #include "nr_math.cuh"
 
 namespace {
@@ -22,15 +23,14 @@ __device__ __forceinline__ int unpack_hi(uint32_t v) { return (int)(short)(v >> 
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 
 // ------------------------------------------------------------------------------------------------ k_face_bbox
-__global__ void __launch_bounds__(kChunk) k_face_bbox(const float* __restrict__ faces, int F, int S, int ngroups,
+__global__ void __launch_bounds__(kChunk) k_face_bbox(const nr::FaceSrc src, int F, int S, int ngroups,
                                                       uint2* __restrict__ bbox, uint2* __restrict__ group_bbox) {
     const int b = blockIdx.y;
     const int f = blockIdx.x * kChunk + threadIdx.x;
     int xlo = 1, xhi = 0, ylo = 1, yhi = 0;  // empty
     if (f < F) {
-        const float* v = faces + ((size_t)b * F + f) * 9;
-        const float x0 = __ldg(v + 0), y0 = __ldg(v + 1), x1 = __ldg(v + 3), y1 = __ldg(v + 4), x2 = __ldg(v + 6),
-                    y2 = __ldg(v + 7);
+        const float *v0 = nr::face_vertex(src, b, f, 0), *v1 = nr::face_vertex(src, b, f, 1), *v2 = nr::face_vertex(src, b, f, 2);
+        const float x0 = __ldg(v0), y0 = __ldg(v0 + 1), x1 = __ldg(v1), y1 = __ldg(v1 + 1), x2 = __ldg(v2), y2 = __ldg(v2 + 1);
         const bool finite = isfinite(x0) && isfinite(y0) && isfinite(x1) && isfinite(y1) && isfinite(x2) && isfinite(y2);
         if (finite && !nr::backside(x0, y0, x1, y1, x2, y2)) {
             const float fS = (float)S;

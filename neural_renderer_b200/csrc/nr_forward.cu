@@ -49,7 +49,8 @@ constexpr int kLiveCap = 1024;  // groups culled against the tile per pass (the 
 constexpr uint32_t kNoRec = 1023;  // z-keys carry (face index << 10 | table slot); 1023 = "not in the table"
 
 struct FwdParams {
-    const float* faces;
+    nr::FaceSrc src;
+    size_t tex_bstride;  // cubes per batch item in `textures` (0 with NR_TEX_SHARED)
     const float* textures;
     const float* bg_batch;
     const float* face_light;
@@ -92,10 +93,8 @@ struct __align__(16) TileShared {
 
 // {inv[9], z[3]} of face fn of batch item b, straight from global memory (survivors beyond the table's capacity)
 __device__ __forceinline__ void face_record(const FwdParams& p, int b, int fn, float inv[9], float z[3]) {
-    const float* v = p.faces + ((size_t)b * p.F + fn) * 9;
     float c[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) c[k] = __ldg(v + k);
+    nr::load_face(p.src, b, fn, c);
     const float fS = (float)p.S;
     nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS), nr::to_pixel(c[4], fS),
                      nr::to_pixel(c[6], fS), nr::to_pixel(c[7], fS), inv);
@@ -134,8 +133,9 @@ __device__ __forceinline__ Shaded shade_pixel(const FwdParams& p, const float (*
     if (p.flags & NR_RETURN_RGB) {
         float z0 = z[0], z1 = z[1], z2 = z[2];
         if (p.flags & NR_TEX_Z_BATCH0) {  // rasterize.py:389 -- vertex depths of batch item 0
-            const float* v0 = p.faces + (size_t)fn * 9;
-            z0 = __ldg(v0 + 2); z1 = __ldg(v0 + 5); z2 = __ldg(v0 + 8);
+            z0 = __ldg(nr::face_vertex(p.src, 0, fn, 0) + 2);
+            z1 = __ldg(nr::face_vertex(p.src, 0, fn, 1) + 2);
+            z2 = __ldg(nr::face_vertex(p.src, 0, fn, 2) + 2);
         }
         const int ts = p.ts;
         const nr::TexCoord tc = nr::texture_coords(w, zp, z0, z1, z2, ts, p.tex_cmp, p.tex_val);
@@ -146,7 +146,7 @@ __device__ __forceinline__ Shaded shade_pixel(const FwdParams& p, const float (*
             ncubes = p.F >> 1;
             if (fn >= ncubes) { cube = fn - ncubes; rev = true; }
         }
-        const float* tex = p.textures + ((size_t)b * ncubes + cube) * (size_t)(ts * ts * ts) * 3;
+        const float* tex = p.textures + ((size_t)b * p.tex_bstride + cube) * (size_t)(ts * ts * ts) * 3;
         float l0 = 1.0f, l1 = 1.0f, l2 = 1.0f;
         const bool lit = p.face_light != nullptr;
         if (lit) {
@@ -262,10 +262,8 @@ __global__ void __launch_bounds__(kThreads, kTL2 == 65 ? 1024 / kThreads : 1) k_
                 const int rank = __popc(m & lt_mask);
                 const int trec = tbase + rank;
                 const uint32_t rec = trec < kTab ? (uint32_t)trec : kNoRec;
-                const float* v = p.faces + ((size_t)b * p.F + f) * 9;
                 float c[9];
-#pragma unroll
-                for (int k = 0; k < 9; k++) c[k] = __ldg(v + k);
+                nr::load_face(p.src, b, f, c);
                 if (rec != kNoRec) {
                     float inv[9];
                     nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS),
@@ -483,7 +481,9 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
     const uint32_t flags = a->flags;
     if (B <= 0 || F <= 0 || S <= 0) return NR_ERR_INVALID_ARG;
     if (!(flags & (NR_RETURN_RGB | NR_RETURN_ALPHA | NR_RETURN_DEPTH))) return NR_ERR_INVALID_ARG;  // rasterize.py:25-27
-    if (!a->faces || !a->face_index_map || !a->weight_map || !a->depth_map) return NR_ERR_INVALID_ARG;
+    if (!a->face_index_map || !a->weight_map || !a->depth_map) return NR_ERR_INVALID_ARG;
+    nr::FaceSrc src{};
+    if (!nr_internal::make_face_src(flags, a->faces, a->vertices, a->face_indices, F, a->num_vertices, &src)) return NR_ERR_INVALID_ARG;
     if (flags & NR_RETURN_RGB) {
         if (!a->textures || !a->rgb_map || ts < 2) return NR_ERR_INVALID_ARG;
         if ((flags & NR_TEX_FILL_BACK) && (F & 1)) return NR_ERR_INVALID_ARG;
@@ -502,11 +502,13 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
 
     {
         nr_internal::LaunchScope ls("k_face_bbox", stream);
-        k_face_bbox<<<dim3(nchunks, B), kChunk, 0, stream>>>(a->faces, F, S, ngroups, bbox, cbox);
+        k_face_bbox<<<dim3(nchunks, B), kChunk, 0, stream>>>(src, F, S, ngroups, bbox, cbox);
     }
 
     FwdParams p{};
-    p.faces = a->faces; p.textures = a->textures; p.bg_batch = a->background_batch;
+    p.src = src;
+    p.tex_bstride = (flags & NR_TEX_SHARED) ? 0 : ((flags & NR_TEX_FILL_BACK) ? (size_t)F / 2 : (size_t)F);
+    p.textures = a->textures; p.bg_batch = a->background_batch;
     p.face_light = (flags & NR_RETURN_RGB) ? a->face_light : nullptr;
     p.bbox = bbox; p.group_bbox = cbox;
     p.fim = a->face_index_map; p.wmap = a->weight_map; p.dmap = a->depth_map; p.rgb = a->rgb_map; p.alpha = a->alpha_map;

@@ -173,9 +173,10 @@ struct FaceGeom {
     int i0, i1, i2;
     bool ok;
 };
-__device__ __forceinline__ FaceGeom face_geom(const float* vertices, const int32_t* faces, int b, int Nv, int Nf, int f) {
+__device__ __forceinline__ FaceGeom face_geom(const float* vertices, const int32_t* faces, int b, int Nv, int Nf, int f,
+                                              uint32_t flags) {
     FaceGeom G;
-    const int32_t* fi = faces + ((size_t)b * Nf + f) * 3;
+    const int32_t* fi = faces + ((size_t)((flags & NR_INDICES_SHARED) ? 0 : b) * Nf + f) * 3;
     G.i0 = __ldg(fi); G.i1 = __ldg(fi + 1); G.i2 = __ldg(fi + 2);
     G.ok = (unsigned)G.i0 < (unsigned)Nv && (unsigned)G.i1 < (unsigned)Nv && (unsigned)G.i2 < (unsigned)Nv;
     float v[3][3] = {};
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(256) k_face_light_fwd(const float* __restrict_
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= Nf) return;
     const LightItem L = load_light(params, (flags & NR_CAM_SHARED) ? 0 : b);
-    const FaceGeom G = face_geom(vertices, faces, b, Nv, Nf, f);
+    const FaceGeom G = face_geom(vertices, faces, b, Nv, Nf, f, flags);
     const float inv = 1.0f / (G.len + 1e-5f);
     const float cosv = fmaxf((G.c[0] * inv * L.dir[0] + G.c[1] * inv * L.dir[1]) + G.c[2] * inv * L.dir[2], 0.0f);
     float* o = light + ((size_t)b * Nf + f) * 3;
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) k_face_light_bwd(const float* __restrict_
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= Nf) return;
     const LightItem L = load_light(params, (flags & NR_CAM_SHARED) ? 0 : b);
-    const FaceGeom G = face_geom(vertices, faces, b, Nv, Nf, f);
+    const FaceGeom G = face_geom(vertices, faces, b, Nv, Nf, f, flags);
     if (!G.ok) return;
     const float inv = 1.0f / (G.len + 1e-5f);
     const float n[3] = {G.c[0] * inv, G.c[1] * inv, G.c[2] * inv};

@@ -35,3 +35,59 @@ def allreduce_shared_grads(params, group=None, async_op=False):
         if async_op:
             works.append(w)
     return works
+
+
+class _PendingAllReduce:
+    """Handle returned to the rasterizer's backward: `.wait()` makes the CURRENT stream wait for the collective."""
+
+    def __init__(self, work):
+        self.work = work
+
+    def wait(self):
+        self.work.wait()
+
+
+class overlap_texture_allreduce:
+    """Context manager: while active, every rasterizer backward on this rank sum-all-reduces its texture gradient
+    across `group` AS SOON AS the texture-gradient kernels are enqueued -- on a side stream, so that the (large)
+    texture all-reduce runs underneath the edge scan / vertex-gradient kernels of the same backward pass instead of
+    behind them ("overlap the texture all-reduce with the vertex-gradient scan").
+
+    How: the C ABI issues the backward in two halves (NR_BWD_PART_TEXTURES, then NR_BWD_PART_FACES).  Between them the
+    side stream picks up the compute stream's position (only the texture half is enqueued at that point) and launches
+    the collective; after the second half is enqueued the compute stream waits for the collective, so what autograd
+    accumulates into `textures.grad` is already the global sum.  The collective is linear, so this is correct for a
+    shared texture set ([1,F,...], NR_TEX_SHARED: 96 MB at 1 M faces / ts 2) and for per-item textures alike.
+    With one rank, or outside an initialised process group, the hook does nothing.
+    """
+
+    def __init__(self, group=None):
+        self.group = group
+        self._streams = {}
+        self._prev = None
+        self.launched = 0  # collectives started (for tests / launch accounting)
+
+    def _hook(self, grad):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return None
+        dev = grad.device
+        side = self._streams.get(dev)
+        if side is None:
+            side = self._streams[dev] = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))  # = the texture half; the edge scan is not enqueued yet
+        with torch.cuda.stream(side):
+            work = dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        grad.record_stream(side)
+        self.launched += 1
+        return _PendingAllReduce(work)
+
+    def __enter__(self):
+        from .rasterize import set_texture_grad_hook
+        self._prev = set_texture_grad_hook(self._hook)
+        return self
+
+    def __exit__(self, *exc):
+        from .rasterize import set_texture_grad_hook
+        set_texture_grad_hook(self._prev)
+        return False

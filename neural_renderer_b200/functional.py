@@ -325,6 +325,8 @@ class _FaceLighting(torch.autograd.Function):
         bs, nv = v.shape[:2]
         nf = faces_i32.shape[1]
         flags = _lib.NR_CAM_SHARED if (params.shape[0] == 1 and bs != 1) else 0
+        if faces_i32.shape[0] == 1 and bs != 1:
+            flags |= _lib.NR_INDICES_SHARED  # one index set for every batch item
         out = torch.empty((bs, nf, 3), dtype=torch.float32, device=v.device)
         with torch.cuda.device(v.device):
             stream = ctypes.c_void_p(torch.cuda.current_stream(v.device).cuda_stream)
@@ -368,6 +370,8 @@ def face_light_from_vertices(vertices, faces, intensity_ambient=0.5, intensity_d
     if params is None:
         row = np.concatenate([np.float32(intensity_ambient) * ca, np.float32(intensity_directional) * cd, d]).astype(np.float32)
         params = _cache_put(key, torch.from_numpy(row[None]).to(vertices.device))
+    if faces.dim() == 3 and faces.shape[0] > 1 and faces.stride(0) == 0:
+        faces = faces[:1]  # expanded shared index set: keep it shared
     return _FaceLighting.apply(vertices, faces.to(torch.int32).contiguous(), params)
 
 

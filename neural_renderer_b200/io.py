@@ -144,15 +144,105 @@ def load_obj(filename_obj, normalization=True, texture_size=4, load_texture=Fals
     return vertices, faces
 
 
+def create_texture_image(textures, texture_size_out=16):
+    """Texture atlas of save_obj.py:10-148: every face gets a texture_size_out^2 tile whose lower-left triangle is the
+    face's barycentric texture cube resampled trilinearly; returns (image [H,W,3] float32, rows already flipped for
+    writing; uv [F,3,2] in [0,1]).  Vectorised numpy restatement of the reference's two CuPy kernels (the resampling
+    pass, then the pass that copies the pixel left of the tile diagonal onto the diagonal's upper neighbour)."""
+    textures = np.asarray(textures, dtype=np.float32)
+    num_faces, tsi = textures.shape[:2]
+    tso = int(texture_size_out)
+    tile_width = int((num_faces - 1.) ** 0.5) + 1
+    tile_height = int((num_faces - 1.) / tile_width) + 1
+    H, W = tile_height * tso, tile_width * tso
+    fn_all = np.arange(num_faces)
+    column, row = fn_all % tile_width, fn_all // tile_width
+    uv = np.zeros((num_faces, 3, 2), np.float32)
+    uv[:, 0, 0] = column * tso
+    uv[:, 0, 1] = row * tso
+    uv[:, 1, 0] = column * tso
+    uv[:, 1, 1] = (row + 1) * tso - 1
+    uv[:, 2, 0] = (column + 1) * tso - 1
+    uv[:, 2, 1] = (row + 1) * tso - 1
+    y, x = np.mgrid[0:H, 0:W]
+    fn = (x // tso) + (y // tso) * tile_width
+    valid = fn < num_faces                      # the reference reads past the arrays for the unused tiles
+    fnc = np.where(valid, fn, 0)
+    p0, p1, p2 = uv[fnc, 0], uv[fnc, 1], uv[fnc, 2]
+    xf, yf = x.astype(np.float32), y.astype(np.float32)
+    den = p2[..., 0] * (p0[..., 1] - p1[..., 1]) + p0[..., 0] * (p1[..., 1] - p2[..., 1]) + p1[..., 0] * (p2[..., 1] - p0[..., 1])
+    inv = np.stack([
+        p1[..., 1] - p2[..., 1], p2[..., 0] - p1[..., 0], p1[..., 0] * p2[..., 1] - p2[..., 0] * p1[..., 1],
+        p2[..., 1] - p0[..., 1], p0[..., 0] - p2[..., 0], p2[..., 0] * p0[..., 1] - p0[..., 0] * p2[..., 1],
+        p0[..., 1] - p1[..., 1], p1[..., 0] - p0[..., 0], p0[..., 0] * p1[..., 1] - p1[..., 0] * p0[..., 1]], axis=-1) / den[..., None]
+    eps = np.float32(1e-5)
+    weight = np.stack([inv[..., 3 * k] * xf + inv[..., 3 * k + 1] * yf + inv[..., 3 * k + 2] for k in range(3)], axis=-1)
+    weight = weight / (weight.sum(-1, keepdims=True) + eps)
+    tif = np.clip(weight * (tsi - 1), 0., tsi - 1 - eps).astype(np.float32)
+    ti = tif.astype(np.int32)
+    frac = tif - ti
+    tex = textures.reshape(num_faces, tsi * tsi * tsi, 3)
+    image = np.zeros((H, W, 3), np.float32)
+    for pn in range(8):
+        wgt = np.ones((H, W), np.float32)
+        idx = []
+        for k in range(3):
+            if (pn >> k) % 2 == 0:
+                wgt = wgt * (1 - frac[..., k])
+                idx.append(ti[..., k])
+            else:
+                wgt = wgt * frac[..., k]
+                idx.append(np.minimum(ti[..., k] + 1, tsi - 1))  # weight 0 whenever the clamp bites
+        isc = idx[0] * tsi * tsi + idx[1] * tsi + idx[2]
+        image += wgt[..., None] * tex[fnc, isc]
+    image[~valid] = 0
+    # second kernel: the pixel just above the tile diagonal takes its left neighbour's colour
+    sel = ((y % tso + 1) == (x % tso))
+    image[sel] = image[y[sel], x[sel] - 1]
+    uv[:, :, 0] /= (W - 1)
+    uv[:, :, 1] /= (H - 1)
+    return image[::-1], uv
+
+
 def save_obj(filename, vertices, faces, textures=None):
-    """Write geometry (v / f lines).  Texture atlas export (save_obj.py:10-148) is outside the hot-path scope."""
+    """Write a Wavefront .obj (save_obj.py:151-191).  With `textures` [F,ts,ts,ts,3] also the texture atlas
+    `<name>.png`, `<name>.mtl` and `vt` / `usemtl` / `f v/vt` lines, so that `load_obj(..., load_texture=True)` reads the
+    mesh back."""
+    vertices = np.asarray(vertices.detach().cpu() if hasattr(vertices, 'detach') else vertices)
+    faces = np.asarray(faces.detach().cpu() if hasattr(faces, 'detach') else faces)
+    assert vertices.ndim == 2
+    assert faces.ndim == 2
     if textures is not None:
-        raise NotImplementedError("texture atlas export is outside the B200 hot path")
-    vertices = np.asarray(vertices)
-    faces = np.asarray(faces)
+        textures = np.asarray(textures.detach().cpu() if hasattr(textures, 'detach') else textures)
+        filename_mtl = filename[:-4] + '.mtl'
+        filename_texture = filename[:-4] + '.png'
+        material_name = 'material_1'
+        texture_image, vertices_textures = create_texture_image(textures)
+        from PIL import Image
+        # scipy.misc.toimage(image, cmin=0, cmax=1): scale to 0..255, clip, round
+        data = (np.clip(texture_image * 255.0, 0, 255) + 0.5).astype(np.uint8)
+        Image.fromarray(data, 'RGB').save(filename_texture)
     with open(filename, 'w') as f:
+        f.write('# %s\n' % os.path.basename(filename))
+        f.write('#\n')
+        f.write('\n')
+        if textures is not None:
+            f.write('mtllib %s\n\n' % os.path.basename(filename_mtl))
         for v in vertices:
             f.write('v %.8f %.8f %.8f\n' % (v[0], v[1], v[2]))
         f.write('\n')
-        for face in faces:
-            f.write('f %d %d %d\n' % (face[0] + 1, face[1] + 1, face[2] + 1))
+        if textures is not None:
+            for v in vertices_textures.reshape((-1, 2)):
+                f.write('vt %.8f %.8f\n' % (v[0], v[1]))
+            f.write('\n')
+            f.write('usemtl %s\n' % material_name)
+            for i, face in enumerate(faces):
+                f.write('f %d/%d %d/%d %d/%d\n' % (face[0] + 1, 3 * i + 1, face[1] + 1, 3 * i + 2, face[2] + 1, 3 * i + 3))
+            f.write('\n')
+        else:
+            for face in faces:
+                f.write('f %d %d %d\n' % (face[0] + 1, face[1] + 1, face[2] + 1))
+    if textures is not None:
+        with open(filename_mtl, 'w') as f:
+            f.write('newmtl %s\n' % material_name)
+            f.write('map_Kd %s\n' % os.path.basename(filename_texture))

@@ -19,7 +19,15 @@ class Mesh(torch.nn.Module):
         self.texture_size = texture_size
 
     def get_batch(self, batch_size):
+        # mesh.py:29-34: broadcast for the minibatch.  The broadcasts are stride-0 views: `Renderer` keeps the index
+        # and texture sets shared (NR_INDICES_SHARED / NR_TEX_SHARED) instead of materialising batch_size copies, and
+        # the sigmoid runs once on the shared set (sigmoid(broadcast(x)) == broadcast(sigmoid(x))).
         vertices = self.vertices[None].expand(batch_size, *self.vertices.shape)
         faces = self.faces[None].expand(batch_size, *self.faces.shape)
-        textures = torch.sigmoid(self.textures[None].expand(batch_size, *self.textures.shape))
+        textures = torch.sigmoid(self.textures)[None].expand(batch_size, *self.textures.shape)
         return vertices, faces, textures
+
+    def set_lr(self, lr_vertices, lr_textures):
+        """mesh.py:36-38: per-parameter learning-rate multipliers honoured by `neural_renderer.Adam`."""
+        self.vertices.lr = lr_vertices
+        self.textures.lr = lr_textures

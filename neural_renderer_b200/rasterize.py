@@ -52,34 +52,65 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def _check_inputs(faces, textures, return_rgb, face_light=None, textures_fill_back=False):
+def _check_inputs(faces, textures, return_rgb, face_light=None, textures_fill_back=False, vertices=None):
     # rasterize.py:66-90 (chainer type_check) -> TypeError / ValueError with the same conditions
     if not isinstance(faces, torch.Tensor):
         raise TypeError("faces must be a torch.Tensor")
-    if not faces.is_floating_point():
-        raise TypeError("faces must be floating point")
-    if faces.dim() != 4 or faces.shape[2] != 3 or faces.shape[3] != 3:
-        raise ValueError("faces must have shape [batch size, num faces, 3, 3], got %s" % (tuple(faces.shape),))
+    if vertices is not None:
+        # indexed geometry (vertices_to_faces.py:10-14 asserts): vertices [B,Nv,3] float, faces [B,F,3] / [1,F,3] / [F,3] int
+        if not isinstance(vertices, torch.Tensor) or not vertices.is_floating_point():
+            raise TypeError("vertices must be a floating point torch.Tensor")
+        if vertices.dim() != 3 or vertices.shape[2] != 3:
+            raise ValueError("vertices must have shape [batch size, num vertices, 3], got %s" % (tuple(vertices.shape),))
+        if faces.is_floating_point():
+            raise TypeError("with `vertices`, faces must hold integer vertex indices")
+        if not ((faces.dim() == 2 and faces.shape[1] == 3)
+                or (faces.dim() == 3 and faces.shape[2] == 3 and faces.shape[0] in (1, vertices.shape[0]))):
+            raise ValueError("with `vertices`, faces must have shape [batch size, num faces, 3] or [num faces, 3], got %s"
+                             % (tuple(faces.shape),))
+        if not vertices.is_cuda or not faces.is_cuda:
+            raise NotImplementedError("neural_renderer_b200 has no CPU implementation (inputs must be CUDA tensors)")
+        batch_size, num_faces = vertices.shape[0], faces.shape[-2]
+    else:
+        if not faces.is_floating_point():
+            raise TypeError("faces must be floating point")
+        if faces.dim() != 4 or faces.shape[2] != 3 or faces.shape[3] != 3:
+            raise ValueError("faces must have shape [batch size, num faces, 3, 3], got %s" % (tuple(faces.shape),))
+        batch_size, num_faces = faces.shape[0], faces.shape[1]
     if return_rgb:
         if not isinstance(textures, torch.Tensor):
             raise TypeError("textures are required to draw RGB")
         if not textures.is_floating_point():
             raise TypeError("textures must be floating point")
-        num_cubes = faces.shape[1] // 2 if textures_fill_back else faces.shape[1]
-        if textures_fill_back and faces.shape[1] % 2:
+        num_cubes = num_faces // 2 if textures_fill_back else num_faces
+        if textures_fill_back and num_faces % 2:
             raise ValueError("textures_fill_back needs an even number of faces (front faces, then their reversed copies)")
+        # batch size 1 with a larger geometry batch = ONE set of cubes shared by every item (a mesh seen from B viewpoints)
         if (textures.dim() != 6 or textures.shape[2] < 2 or textures.shape[2] != textures.shape[3]
                 or textures.shape[3] != textures.shape[4] or textures.shape[5] != 3
-                or textures.shape[0] != faces.shape[0] or textures.shape[1] != num_cubes):
+                or textures.shape[0] not in (1, batch_size) or textures.shape[1] != num_cubes):
             raise ValueError("textures must have shape [batch size, num faces, ts, ts, ts, 3] with ts >= 2 and match "
                              "faces, got %s" % (tuple(textures.shape),))
     if return_rgb and face_light is not None:
-        if not isinstance(face_light, torch.Tensor) or tuple(face_light.shape) != (faces.shape[0], faces.shape[1], 3):
+        if not isinstance(face_light, torch.Tensor) or tuple(face_light.shape) != (batch_size, num_faces, 3):
             raise ValueError("face_light must have shape [batch size, num faces, 3]")
         if not face_light.is_cuda:
             raise NotImplementedError("neural_renderer_b200 has no CPU implementation (inputs must be CUDA tensors)")
     if not faces.is_cuda or (return_rgb and not textures.is_cuda):
         raise NotImplementedError("neural_renderer_b200 has no CPU implementation (inputs must be CUDA tensors)")
+
+
+# Optional hook between the two halves of the backward pass (neural_renderer_b200.distributed.overlap_texture_allreduce):
+# called as hook(grad_textures) right after the texture-gradient kernels are enqueued and BEFORE the edge scan is;
+# returns an object whose .wait() is called once the whole pass is enqueued.
+_TEXTURE_GRAD_HOOK = None
+
+
+def set_texture_grad_hook(hook):
+    global _TEXTURE_GRAD_HOOK
+    prev = _TEXTURE_GRAD_HOOK
+    _TEXTURE_GRAD_HOOK = hook
+    return prev
 
 
 class _Config:
@@ -132,22 +163,35 @@ def _stream_ptr(device):
 class _RasterizeFunction(torch.autograd.Function):
     """autograd node of the hot path: forward = nr_b200_forward, backward = nr_b200_backward.
 
-    Outputs are the API images (planar, image orientation, pooled when anti-aliasing) plus the raster-resolution
-    maps (returned non-differentiable so tests / the `Rasterize` object can look at them)."""
+    `geom` is faces [B,F,3,3], or -- indexed geometry, `indices` given -- vertices [B,Nv,3] (the vertices_to_faces
+    gather and its scatter-add backward happen inside the kernels).  Outputs are the API images (planar, image
+    orientation, pooled when anti-aliasing) plus the raster-resolution maps (returned non-differentiable so tests /
+    the `Rasterize` object can look at them)."""
 
     @staticmethod
-    def forward(ctx, faces, textures, face_light, cfg):
+    def forward(ctx, geom, textures, face_light, cfg, indices):
         lib = _lib.load()
-        dev = faces.device
-        faces_c = faces.detach().contiguous()
+        dev = geom.device
+        geom_c = geom.detach().contiguous()
         tex_c = textures.detach().contiguous() if textures is not None else None
         light_c = face_light.detach().to(torch.float32).contiguous() if face_light is not None else None
-        B, F = faces_c.shape[:2]
+        flags = cfg.flags
+        if indices is not None:
+            B, Nv = geom_c.shape[:2]
+            F = indices.shape[-2]
+            flags |= _lib.NR_FACES_INDEXED
+            if indices.dim() == 2 or (indices.shape[0] == 1 and B > 1):
+                flags |= _lib.NR_INDICES_SHARED
+        else:
+            B, F = geom_c.shape[:2]
+            Nv = 0
+        if tex_c is not None and tex_c.shape[0] == 1 and B > 1:
+            flags |= _lib.NR_TEX_SHARED
         S = cfg.S
         ts = int(tex_c.shape[2]) if tex_c is not None else 0
-        want_rgb = bool(cfg.flags & _lib.NR_RETURN_RGB)
-        want_alpha = bool(cfg.flags & _lib.NR_RETURN_ALPHA)
-        want_depth = bool(cfg.flags & _lib.NR_RETURN_DEPTH)
+        want_rgb = bool(flags & _lib.NR_RETURN_RGB)
+        want_alpha = bool(flags & _lib.NR_RETURN_ALPHA)
+        want_depth = bool(flags & _lib.NR_RETURN_DEPTH)
         with torch.cuda.device(dev):
             fim = torch.empty((B, S, S), dtype=torch.int32, device=dev)
             wmap = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
@@ -163,15 +207,19 @@ class _RasterizeFunction(torch.autograd.Function):
                     out_alpha = torch.empty((B, H, H), dtype=torch.float32, device=dev)
                 if want_depth:
                     out_depth = torch.empty((B, H, H), dtype=torch.float32, device=dev)
-            ws_bytes = lib.nr_b200_forward_workspace_bytes(B, F, S, ts, cfg.flags)
+            ws_bytes = lib.nr_b200_forward_workspace_bytes(B, F, S, ts, flags)
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
             a = _lib.ForwardArgs()
             a.struct_size = ctypes.sizeof(_lib.ForwardArgs)
-            a.flags = cfg.flags
+            a.flags = flags
             a.batch_size, a.num_faces, a.raster_size, a.texture_size = B, F, S, ts
             a.near_, a.far_, a.eps = cfg.near, cfg.far, cfg.eps
             a.background[0], a.background[1], a.background[2] = cfg.bg
-            a.faces, a.textures, a.background_batch = _ptr(faces_c), _ptr(tex_c), _ptr(cfg.bg_batch)
+            if indices is not None:
+                a.vertices, a.face_indices, a.num_vertices = _ptr(geom_c), _ptr(indices), Nv
+            else:
+                a.faces = _ptr(geom_c)
+            a.textures, a.background_batch = _ptr(tex_c), _ptr(cfg.bg_batch)
             a.face_index_map, a.weight_map, a.depth_map = _ptr(fim), _ptr(wmap), _ptr(dmap)
             a.rgb_map, a.alpha_map = _ptr(rgb_map), _ptr(alpha_map)
             a.out_rgb, a.out_alpha, a.out_depth = _ptr(out_rgb), _ptr(out_alpha), _ptr(out_depth)
@@ -179,11 +227,13 @@ class _RasterizeFunction(torch.autograd.Function):
             a.face_light = _ptr(light_c)
             _lib.check(lib.nr_b200_forward(ctypes.byref(a), _stream_ptr(dev)))
         ctx.cfg = cfg
+        ctx.flags = flags
         ctx.ts = ts
+        ctx.F = F
         ctx.tex_shape = tuple(textures.shape) if textures is not None else None
         # the unlit textures are only needed again for d loss / d face_light
         need_light_grad = light_c is not None and ctx.needs_input_grad[2]
-        ctx.save_for_backward(faces_c, fim, wmap, dmap, rgb_map, light_c, tex_c if need_light_grad else None)
+        ctx.save_for_backward(geom_c, fim, wmap, dmap, rgb_map, light_c, tex_c if need_light_grad else None, indices)
         if cfg.aa:
             rgb_o, alpha_o, depth_o = out_rgb, out_alpha, out_depth
         else:
@@ -195,10 +245,11 @@ class _RasterizeFunction(torch.autograd.Function):
     def backward(ctx, g_rgb, g_alpha, g_depth, _g_fim, _g_wmap):
         lib = _lib.load()
         cfg = ctx.cfg
-        faces_c, fim, wmap, dmap, rgb_map, light_c, tex_c = ctx.saved_tensors
-        dev = faces_c.device
-        B, F = faces_c.shape[:2]
-        want_rgb = bool(cfg.flags & _lib.NR_RETURN_RGB)
+        flags = ctx.flags
+        geom_c, fim, wmap, dmap, rgb_map, light_c, tex_c, indices = ctx.saved_tensors
+        dev = geom_c.device
+        B, F = geom_c.shape[0], ctx.F
+        want_rgb = bool(flags & _lib.NR_RETURN_RGB)
 
         def prep(g, wanted):
             if g is None or not wanted:
@@ -206,41 +257,70 @@ class _RasterizeFunction(torch.autograd.Function):
             return g.detach().to(torch.float32).contiguous()
 
         g_rgb = prep(g_rgb, want_rgb)
-        g_alpha = prep(g_alpha, bool(cfg.flags & _lib.NR_RETURN_ALPHA))
-        g_depth = prep(g_depth, bool(cfg.flags & _lib.NR_RETURN_DEPTH))
+        g_alpha = prep(g_alpha, bool(flags & _lib.NR_RETURN_ALPHA))
+        g_depth = prep(g_depth, bool(flags & _lib.NR_RETURN_DEPTH))
         with torch.cuda.device(dev):
-            grad_faces = torch.empty_like(faces_c)
+            grad_geom = torch.empty_like(geom_c)  # grad_faces [B,F,3,3], or grad_vertices [B,Nv,3] when indexed
             grad_textures = torch.empty(ctx.tex_shape, dtype=torch.float32, device=dev) if want_rgb else None
             grad_light = torch.empty_like(light_c) if (want_rgb and tex_c is not None) else None
-            ws_bytes = lib.nr_b200_backward_workspace_bytes(B, F, cfg.S, ctx.ts, cfg.flags)
+            ws_bytes = lib.nr_b200_backward_workspace_bytes(B, F, cfg.S, ctx.ts, flags)
             ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
             a = _lib.BackwardArgs()
             a.struct_size = ctypes.sizeof(_lib.BackwardArgs)
-            a.flags = cfg.flags
             a.batch_size, a.num_faces, a.raster_size, a.texture_size = B, F, cfg.S, ctx.ts
             a.eps = cfg.eps
-            a.faces, a.textures = _ptr(faces_c), _ptr(tex_c)
+            if indices is not None:
+                a.vertices, a.face_indices, a.num_vertices = _ptr(geom_c), _ptr(indices), geom_c.shape[1]
+                a.grad_vertices = _ptr(grad_geom)
+            else:
+                a.faces, a.grad_faces = _ptr(geom_c), _ptr(grad_geom)
+            a.textures = _ptr(tex_c)
             a.face_light, a.grad_face_light = _ptr(light_c), _ptr(grad_light)
             a.face_index_map, a.weight_map, a.depth_map, a.rgb_map = _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(rgb_map)
             a.grad_rgb, a.grad_alpha, a.grad_depth = _ptr(g_rgb), _ptr(g_alpha), _ptr(g_depth)
-            a.grad_faces, a.grad_textures = _ptr(grad_faces), _ptr(grad_textures)
+            a.grad_textures = _ptr(grad_textures)
             a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
-            _lib.check(lib.nr_b200_backward(ctypes.byref(a), _stream_ptr(dev)))
-        return grad_faces, grad_textures, grad_light, None
+            hook = _TEXTURE_GRAD_HOOK if (want_rgb and g_rgb is not None) else None
+            if hook is None:
+                a.flags = flags
+                _lib.check(lib.nr_b200_backward(ctypes.byref(a), _stream_ptr(dev)))
+            else:
+                # two halves: the texture gradient is complete (and may start its all-reduce on another stream)
+                # before the edge scan is even enqueued
+                a.flags = flags | _lib.NR_BWD_PART_TEXTURES
+                _lib.check(lib.nr_b200_backward(ctypes.byref(a), _stream_ptr(dev)))
+                pending = hook(grad_textures)
+                a.flags = flags | _lib.NR_BWD_PART_FACES
+                _lib.check(lib.nr_b200_backward(ctypes.byref(a), _stream_ptr(dev)))
+                if pending is not None:
+                    pending.wait()
+        return grad_geom, grad_textures, grad_light, None, None
 
 
 def _run(faces, textures, image_size, anti_aliasing, near, far, eps, background_color, return_rgb, return_alpha,
-         return_depth, face_light=None, textures_fill_back=False):
-    _check_inputs(faces, textures, return_rgb, face_light, textures_fill_back)
-    if faces.dtype != torch.float32:
-        faces = faces.float()
-    if return_rgb and textures.dtype != torch.float32:
-        textures = textures.float()
+         return_depth, face_light=None, textures_fill_back=False, vertices=None):
+    _check_inputs(faces, textures, return_rgb, face_light, textures_fill_back, vertices)
+    indices = None
+    if vertices is not None:
+        geom = vertices if vertices.dtype == torch.float32 else vertices.float()
+        indices = faces
+        if indices.dim() == 3 and indices.shape[0] > 1 and indices.stride(0) == 0:
+            indices = indices[:1]  # an expanded [F,3] index set (Mesh.get_batch): keep it shared, do not materialise
+        indices = indices.to(torch.int32).contiguous()
+    else:
+        geom = faces if faces.dtype == torch.float32 else faces.float()
+    batch_size = geom.shape[0]
+    if return_rgb:
+        if textures.dtype != torch.float32:
+            textures = textures.float()
+        if textures.shape[0] == batch_size > 1 and textures.stride(0) == 0:
+            textures = textures[:1]  # an expanded shared texture set: sample it in place (NR_TEX_SHARED)
     cfg = _make_config(image_size, anti_aliasing, near, far, eps, background_color, return_rgb, return_alpha,
-                       return_depth, faces.device, faces.shape[0])
+                       return_depth, geom.device, batch_size)
     if return_rgb and textures_fill_back:
         cfg.flags |= _lib.NR_TEX_FILL_BACK
-    return _RasterizeFunction.apply(faces, textures if return_rgb else None, face_light if return_rgb else None, cfg)
+    return _RasterizeFunction.apply(geom, textures if return_rgb else None, face_light if return_rgb else None, cfg,
+                                    indices)
 
 
 def rasterize_rgbad(
@@ -258,6 +338,7 @@ def rasterize_rgbad(
         *,
         face_light=None,
         textures_fill_back=False,
+        vertices=None,
 ):
     """Generate RGB, alpha channel, and depth images from faces and textures (for RGB).  rasterize.py:900-977.
 
@@ -267,9 +348,15 @@ def rasterize_rgbad(
     fill_back-doubled texture tensor is ever materialised):
       face_light [B,F,3]      per-face RGB factor of `lighting` applied at sample time (== sampling textures * light)
       textures_fill_back      faces [F/2, F) are the reversed copies of [0, F/2) and `textures` holds only the F/2
-                              original cubes (the copies read them with reversed axes, renderer.py:80)"""
+                              original cubes (the copies read them with reversed axes, renderer.py:80)
+      vertices [B,Nv,3]       indexed geometry: `faces` then holds integer vertex indices ([B,F,3], or [F,3] / [1,F,3]
+                              shared by the batch) and vertices_to_faces (vertices_to_faces.py:16-21) plus its
+                              scatter-add backward run inside the rasterizer: no [B,F,3,3] tensor exists and the
+                              gradient arrives in `vertices.grad`
+    `textures` with batch size 1 (or an expanded stride-0 batch) while the geometry batch is larger = one texture set
+    shared by every item (a mesh seen from B viewpoints, mesh.py:29-34); its gradient is the sum over the items."""
     rgb, alpha, depth, _, _ = _run(faces, textures, image_size, anti_aliasing, near, far, eps, background_color,
-                                   return_rgb, return_alpha, return_depth, face_light, textures_fill_back)
+                                   return_rgb, return_alpha, return_depth, face_light, textures_fill_back, vertices)
     return {
         'rgb': rgb if return_rgb else None,
         'alpha': alpha if return_alpha else None,
@@ -289,11 +376,12 @@ def rasterize(
         *,
         face_light=None,
         textures_fill_back=False,
+        vertices=None,
 ):
     """RGB images [B,3,H,W] from faces and textures.  rasterize.py:980-1008 (keyword-only extras: rasterize_rgbad)."""
     return rasterize_rgbad(
         faces, textures, image_size, anti_aliasing, near, far, eps, background_color, True, False, False,
-        face_light=face_light, textures_fill_back=textures_fill_back)['rgb']
+        face_light=face_light, textures_fill_back=textures_fill_back, vertices=vertices)['rgb']
 
 
 def rasterize_silhouettes(
@@ -303,9 +391,12 @@ def rasterize_silhouettes(
         near=DEFAULT_NEAR,
         far=DEFAULT_FAR,
         eps=DEFAULT_EPS,
+        *,
+        vertices=None,
 ):
-    """Alpha channels [B,H,W] from faces.  rasterize.py:1011-1034."""
-    return rasterize_rgbad(faces, None, image_size, anti_aliasing, near, far, eps, None, False, True, False)['alpha']
+    """Alpha channels [B,H,W] from faces.  rasterize.py:1011-1034 (keyword-only `vertices`: rasterize_rgbad)."""
+    return rasterize_rgbad(faces, None, image_size, anti_aliasing, near, far, eps, None, False, True, False,
+                           vertices=vertices)['alpha']
 
 
 def rasterize_depth(
@@ -315,9 +406,12 @@ def rasterize_depth(
         near=DEFAULT_NEAR,
         far=DEFAULT_FAR,
         eps=DEFAULT_EPS,
+        *,
+        vertices=None,
 ):
-    """Depth images [B,H,W] from faces.  rasterize.py:1037-1060."""
-    return rasterize_rgbad(faces, None, image_size, anti_aliasing, near, far, eps, None, False, False, True)['depth']
+    """Depth images [B,H,W] from faces.  rasterize.py:1037-1060 (keyword-only `vertices`: rasterize_rgbad)."""
+    return rasterize_rgbad(faces, None, image_size, anti_aliasing, near, far, eps, None, False, False, True,
+                           vertices=vertices)['depth']
 
 
 class Rasterize(object):

@@ -44,7 +44,24 @@ class Renderer(object):
         return F.camera_transform(vertices, self.eye, self.camera_mode, self.camera_direction, self.perspective,
                                   self.viewing_angle)
 
+    @staticmethod
+    def _fusable(vertices, faces):
+        return vertices.is_cuda and faces.is_cuda and vertices.dtype == torch.float32 and not faces.is_floating_point()
+
+    def _indices(self, faces):
+        """Face indices as the rasterizer consumes them: a shared (expanded, stride-0) index set stays [1,F,3];
+        fill_back appends the reversed copies (renderer.py:38-39) -- index data only, no vertex data is duplicated."""
+        if faces.dim() == 3 and faces.shape[0] > 1 and faces.stride(0) == 0:
+            faces = faces[:1]
+        if self.fill_back:
+            faces = torch.cat((faces, faces.flip(2)), dim=1)
+        return faces
+
     def render_silhouettes(self, vertices, faces):
+        if self.fused and self._fusable(vertices, faces):
+            # vertices_to_faces (renderer.py:51) runs inside the rasterizer: no [B,F,3,3] tensor on either pass
+            return rasterize_silhouettes(self._indices(faces), self.image_size, self.anti_aliasing,
+                                         vertices=self._transform(vertices))
         if self.fill_back:
             faces = torch.cat((faces, faces.flip(2)), dim=1)
         vertices = self._transform(vertices)
@@ -53,6 +70,9 @@ class Renderer(object):
         return rasterize_silhouettes(faces, self.image_size, self.anti_aliasing)
 
     def render_depth(self, vertices, faces):
+        if self.fused and self._fusable(vertices, faces):
+            return rasterize_depth(self._indices(faces), self.image_size, self.anti_aliasing,
+                                   vertices=self._transform(vertices))
         if self.fill_back:
             faces = torch.cat((faces, faces.flip(2)), dim=1)
         vertices = self._transform(vertices)
@@ -60,23 +80,22 @@ class Renderer(object):
         return rasterize_depth(faces, self.image_size, self.anti_aliasing)  # renderer.py:72
 
     def render(self, vertices, faces, textures):
-        fused = (self.fused and vertices.is_cuda and textures.is_cuda and vertices.dtype == torch.float32
-                 and textures.dtype == torch.float32)
-        if self.fill_back:
-            faces = torch.cat((faces, faces.flip(2)), dim=1)
-            if not fused:
-                textures = torch.cat((textures, textures.permute(0, 1, 4, 3, 2, 5)), dim=1)
+        fused = (self.fused and self._fusable(vertices, faces) and textures.is_cuda and textures.dtype == torch.float32)
         light_args = (self.light_intensity_ambient, self.light_intensity_directional, self.light_color_ambient,
                       self.light_color_directional, self.light_direction)
         if fused:
-            # lighting.py:29-52 and renderer.py:78-80 folded into the sampler: neither `textures * light` nor the
-            # doubled texture tensor exists; pixel values are bit-identical to the op-by-op formulation
-            light = F.face_light_from_vertices(vertices, faces, *light_args)
-            vertices = self._transform(vertices)
-            faces = F.vertices_to_faces(vertices, faces)
+            # lighting.py:29-52, renderer.py:78-80 and vertices_to_faces (renderer.py:103) folded into the rasterizer:
+            # neither `textures * light`, nor the doubled texture tensor, nor faces [B,F,3,3] exist; pixel values are
+            # bit-identical to the op-by-op formulation
+            indices = self._indices(faces)
+            light = F.face_light_from_vertices(vertices, indices, *light_args)
             return rasterize(
-                faces, textures, self.image_size, self.anti_aliasing, self.near, self.far, self.rasterizer_eps,
-                self.background_color, face_light=light, textures_fill_back=self.fill_back)
+                indices, textures, self.image_size, self.anti_aliasing, self.near, self.far, self.rasterizer_eps,
+                self.background_color, face_light=light, textures_fill_back=self.fill_back,
+                vertices=self._transform(vertices))
+        if self.fill_back:
+            faces = torch.cat((faces, faces.flip(2)), dim=1)
+            textures = torch.cat((textures, textures.permute(0, 1, 4, 3, 2, 5)), dim=1)
         textures = F.lighting(F.vertices_to_faces(vertices, faces), textures, *light_args)
         vertices = self._transform(vertices)
         faces = F.vertices_to_faces(vertices, faces)

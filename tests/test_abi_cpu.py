@@ -113,3 +113,23 @@ def test_ctypes_structs_match_the_header(tmp_path):
     want = [ctypes.sizeof(_lib.ForwardArgs), _lib.ForwardArgs.faces.offset, _lib.ForwardArgs.face_light.offset,
             ctypes.sizeof(_lib.BackwardArgs), _lib.BackwardArgs.faces.offset, _lib.BackwardArgs.grad_face_light.offset]
     assert got == want
+
+
+def test_no_environment_switches_in_the_product_build():
+    """Ablation / tuning knobs exist only behind NR_B200_DEBUG_KNOBS / NR_B200_TUNING (off in the product build): a
+    stray environment variable must not be able to change what the library computes."""
+    import re
+    csrc = os.path.join(ROOT, "neural_renderer_b200", "csrc")
+    for name in os.listdir(csrc):
+        depth, guarded = [], 0
+        for line in open(os.path.join(csrc, name)):
+            s = line.strip()
+            if re.match(r"#\s*if", s):
+                depth.append(bool(re.search(r"NR_B200_(DEBUG_KNOBS|TUNING)", s)))
+            elif re.match(r"#\s*endif", s) and depth:
+                depth.pop()
+            elif "getenv" in s and not s.startswith("//"):
+                assert any(depth), "%s: getenv outside a knob guard: %s" % (name, s)
+                guarded += 1
+    from neural_renderer_b200 import build
+    assert not any("NR_B200_DEBUG_KNOBS" in f or "NR_B200_TUNING" in f for f in build.NVCC_FLAGS)

@@ -4,6 +4,7 @@ import os
 import sys
 
 import numpy as np
+import pytest
 import torch
 
 import nr_oracle as o
@@ -149,3 +150,94 @@ def test_reference_known_answers_load_obj(tmp_path, teapot):
     assert np.allclose(v, v_ref * 2 - 1.0) and np.array_equal(f, f_ref)
     tv, tf = teapot
     assert tf.shape[0] == 2464 and tv.shape[0] == 1292
+
+
+def test_save_obj_with_textures_round_trip(tmp_path, monkeypatch, teapot):
+    """save_obj(filename, vertices, faces, textures) (save_obj.py:10-191: atlas PNG + .mtl + vt / usemtl / f v/vt) and
+    back through load_obj(load_texture=True): geometry exact, per-face textures within the atlas' 16-pixel tiles'
+    resampling error (smooth textures: a few 8-bit levels)."""
+    import nr_oracle as o
+    from neural_renderer_b200 import io
+    monkeypatch.setattr(io, "bake_textures", lambda image, uv, upd, ts, tex: o.bake_textures(image, uv, upd, ts, tex))
+    v, f = teapot
+    f = f[:300]
+    ts = 4
+    # a smooth per-face texture: colour = barycentric position inside the cube, scaled per face
+    g = np.linspace(0, 1, ts, dtype=np.float32)
+    cube = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1)                       # [ts,ts,ts,3]
+    scale = np.random.default_rng(0).uniform(0.3, 1.0, size=(f.shape[0], 1, 1, 1, 3)).astype(np.float32)
+    textures = cube[None] * scale
+    path = str(tmp_path / "m.obj")
+    io.save_obj(path, v, f, textures)
+    for ext in (".obj", ".mtl", ".png"):
+        assert os.path.exists(path[:-4] + ext)
+    text = open(path).read()
+    assert text.startswith("# m.obj\n#\n\nmtllib m.mtl\n") and "usemtl material_1" in text
+    assert open(path[:-4] + ".mtl").read() == "newmtl material_1\nmap_Kd m.png\n"
+    v2, f2, t2 = io.load_obj(path, normalization=False, texture_size=ts, load_texture=True)
+    assert np.array_equal(f2, f) and np.allclose(v2, v, atol=1e-6)
+    assert t2.shape == textures.shape
+    # texels on the barycentric plane a + b + c = ts - 1 are the ones a face ever samples (weights sum to 1)
+    a, b, c = np.meshgrid(np.arange(ts), np.arange(ts), np.arange(ts), indexing="ij")
+    plane = (a + b + c) == ts - 1
+    err = np.abs(t2[:, plane] - textures[:, plane])
+    assert float(np.nanmax(err)) < 0.12 and float(np.nanmean(err)) < 0.03
+
+
+def test_texture_atlas_layout():
+    from neural_renderer_b200 import io
+    tex = np.zeros((5, 2, 2, 2, 3), np.float32)
+    tex[3] = 1.0
+    image, uv = io.create_texture_image(tex, texture_size_out=8)
+    assert image.shape == (16, 24, 3) and uv.shape == (5, 3, 2)      # 3 x 2 tiles of 8 pixels
+    assert uv.min() >= 0 and uv.max() <= 1
+    up = image[::-1]                                                   # un-flip: tile (row 1, column 0) is face 3
+    assert abs(up[8:16, 0:8].max() - 1.0) < 1e-5 and up[0:8].max() == 0.0 and up[8:16, 8:].max() == 0.0
+
+
+def test_adam_masks_zero_gradients_and_honours_param_lr():
+    """optimizers.py:9-39: elements with grad == 0 keep parameter and both moments; lr = self.lr * param.lr."""
+    import torch
+    from neural_renderer_b200.optimizers import Adam
+    p = torch.nn.Parameter(torch.tensor([1.0, 2.0, 3.0, 4.0]))
+    q = torch.nn.Parameter(torch.tensor([1.0, 2.0]))
+    q.lr = 0.0
+    opt = Adam([p, q], lr=0.1, betas=(0.9, 0.999))
+    p.grad = torch.tensor([0.5, 0.0, -0.25, 0.0])
+    q.grad = torch.tensor([1.0, 1.0])
+    opt.step()
+    # first Adam step moves by lr * sign(g) (bias-corrected), untouched where g == 0; q.lr = 0 freezes q
+    np.testing.assert_allclose(p.detach().numpy(), [0.9, 2.0, 3.1, 4.0], rtol=1e-5)
+    assert torch.equal(q.detach(), torch.tensor([1.0, 2.0]))
+    m = opt.state[p]["m"].clone()
+    p.grad = torch.tensor([0.0, 1.0, 0.0, 0.0])
+    opt.step()
+    assert opt.state[p]["m"][0] == m[0] and opt.state[p]["m"][2] == m[2]        # moments frozen where grad == 0
+    assert p[0].item() == pytest.approx(0.9) and p[1].item() < 2.0
+    # a closure's gradients define the mask (not the stale ones from before the call)
+    p.grad = torch.tensor([1.0, 1.0, 1.0, 1.0])
+    before = p.detach().clone()
+
+    def closure():
+        p.grad = torch.tensor([0.0, 0.0, 0.0, 2.0])
+        return torch.tensor(0.0)
+    opt.step(closure)
+    assert torch.equal(p.detach()[:3], before[:3]) and p[3].item() < before[3].item()
+
+
+def test_mesh_get_batch_is_a_broadcast_and_set_lr(tmp_path, teapot):
+    import torch
+    from neural_renderer_b200 import io
+    from neural_renderer_b200.mesh import Mesh
+    v, f = teapot
+    path = str(tmp_path / "t.obj")
+    io.save_obj(path, v, f)
+    mesh = Mesh(path, texture_size=2)
+    vv, ff, tt = mesh.get_batch(3)
+    assert vv.shape == (3, v.shape[0], 3) and ff.shape == (3, f.shape[0], 3) and tt.shape == (3, f.shape[0], 2, 2, 2, 3)
+    assert vv.stride(0) == 0 and ff.stride(0) == 0 and tt.stride(0) == 0      # views, not copies (mesh.py:29-34)
+    assert torch.equal(tt[1], torch.sigmoid(mesh.textures))
+    tt.sum().backward()
+    assert torch.allclose(mesh.textures.grad, 3 * torch.sigmoid(mesh.textures) * (1 - torch.sigmoid(mesh.textures)), atol=1e-6)
+    mesh.set_lr(0.5, 2.0)
+    assert mesh.vertices.lr == 0.5 and mesh.textures.lr == 2.0

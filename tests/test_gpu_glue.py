@@ -273,3 +273,182 @@ def test_load_obj_with_textures_and_render():
     image = r.render(torch.from_numpy(v)[None].to(dev), torch.from_numpy(f)[None].to(dev), torch.from_numpy(tex)[None].to(dev))
     assert image.shape == (1, 3, 64, 64) and torch.isfinite(image).all()  # texel (0,0,0) (NaN) is never sampled at ts = 4
     assert float(image.max()) > 0.1
+
+
+# ---------------------------------------------------------------------- ABI 3: geometry and textures without copies
+def _indexed_case(B, nv_scale=1.0, seed=0):
+    from neural_renderer_b200 import synthetic
+    v_np, f_np = synthetic.sphere_mesh(1800)
+    rng = np.random.default_rng(seed)
+    vs = []
+    for b in range(B):
+        v = (v_np * 0.7) @ synthetic._rotation(rng).T
+        v[:, 2] += 2.6
+        vs.append(v.astype(np.float32))
+    return np.stack(vs), f_np
+
+
+@pytest.mark.parametrize("flags", [(1, 1, 1), (0, 1, 0), (0, 0, 1)], ids=["rgb_alpha_depth", "alpha", "depth"])
+@pytest.mark.parametrize("shared_idx", [False, True], ids=["idx_per_item", "idx_shared"])
+def test_indexed_geometry_matches_materialised_faces(flags, shared_idx):
+    """NR_FACES_INDEXED: rasterize(indices, ..., vertices=v) == rasterize(vertices_to_faces(v, indices), ...): the maps
+    bit for bit (the same floats reach the same expressions), d loss / d vertices up to the order of the atomics --
+    vertices_to_faces.py:16-21 and its get_item backward folded into the kernels."""
+    import importlib
+    import neural_renderer as nr
+    R = importlib.import_module("neural_renderer_b200.rasterize")
+    dev = torch.device("cuda")
+    B = 3
+    v_np, f_np = _indexed_case(B, seed=4)
+    idx = torch.from_numpy(f_np).to(dev)
+    idx_b = idx[None].expand(B, -1, -1).contiguous()
+    tex = torch.rand((B, f_np.shape[0], 2, 2, 2, 3), generator=torch.Generator().manual_seed(1)).to(dev)
+    bg = (0.2, 0.1, 0.3)
+
+    def run(indexed):
+        v = torch.from_numpy(v_np).to(dev).requires_grad_(True)
+        t = tex.clone().requires_grad_(True)
+        if indexed:
+            out = R._run(idx if shared_idx else idx_b, t if flags[0] else None, 64, False, 0.1, 100, 1e-4, bg, *flags, vertices=v)
+        else:
+            out = R._run(nr.vertices_to_faces(v, idx_b), t if flags[0] else None, 64, False, 0.1, 100, 1e-4, bg, *flags)
+        gen = torch.Generator().manual_seed(9)
+        loss = 0
+        for o in out[:3]:
+            if o is not None:
+                loss = loss + (o * torch.randn(o.shape, generator=gen).to(dev)).sum()
+        loss.backward()
+        return out, v.grad, t.grad
+
+    a, gva, gta = run(True)
+    b, gvb, gtb = run(False)
+    for x, y in zip(a, b):
+        assert (x is None) == (y is None)
+        if x is not None:
+            assert torch.equal(x, y)
+    assert rel_err(gva.cpu(), gvb.cpu()) <= 1e-5
+    if flags[0]:
+        assert rel_err(gta.cpu(), gtb.cpu()) <= 1e-6
+
+
+def test_indexed_geometry_out_of_range_indices_read_zero_vertices():
+    """like nr_b200_vertices_to_faces: an index outside [0, Nv) gathers a vertex of zeros and receives no gradient"""
+    import importlib
+    R = importlib.import_module("neural_renderer_b200.rasterize")
+    dev = torch.device("cuda")
+    v_np, f_np = _indexed_case(1, seed=5)
+    f_bad = f_np.copy()
+    f_bad[::7, 1] = v_np.shape[1] + 5
+    f_bad[3::11, 0] = -1
+    v = torch.from_numpy(v_np).to(dev).requires_grad_(True)
+    out = R._run(torch.from_numpy(f_bad).to(dev), None, 64, False, 0.1, 100, 1e-4, None, False, True, False, vertices=v)
+    faces = torch.zeros((1, f_bad.shape[0], 3, 3), device=dev)
+    ok = (f_bad >= 0) & (f_bad < v_np.shape[1])
+    gathered = v.detach()[0][torch.from_numpy(np.where(ok, f_bad, 0)).to(dev).long()]
+    faces[0] = torch.where(torch.from_numpy(ok).to(dev)[..., None], gathered, torch.zeros((), device=dev))
+    ref = R._run(faces, None, 64, False, 0.1, 100, 1e-4, None, False, True, False)
+    assert torch.equal(out[1], ref[1]) and torch.equal(out[3], ref[3])
+    (out[1] * torch.randn(out[1].shape, generator=torch.Generator().manual_seed(2)).to(dev)).sum().backward()
+    assert torch.isfinite(v.grad).all()
+
+
+@pytest.mark.parametrize("fill_back", [False, True])
+def test_shared_textures_match_expanded_copy(fill_back):
+    """NR_TEX_SHARED: textures [1,F,...] (or an expanded stride-0 batch) sampled in place == the materialised
+    [B,F,...] copy; the gradient is the sum over the batch items (Mesh.get_batch's broadcast backward, mesh.py:29-34)."""
+    import importlib
+    R = importlib.import_module("neural_renderer_b200.rasterize")
+    dev = torch.device("cuda")
+    B = 4
+    v_np, f_np = _indexed_case(B, seed=6)
+    idx = torch.from_numpy(f_np).to(dev)
+    if fill_back:
+        idx = torch.cat((idx, idx.flip(1)), dim=0)
+    ncube = f_np.shape[0]
+    base = torch.rand((ncube, 2, 2, 2, 3), generator=torch.Generator().manual_seed(3)).to(dev)
+    g = torch.randn((B, 3, 64, 64), generator=torch.Generator().manual_seed(4)).to(dev)
+    light = torch.rand((B, idx.shape[0], 3), generator=torch.Generator().manual_seed(5)).to(dev)
+    res = {}
+    for kind in ("copy", "batch1", "expanded"):
+        t0 = base.clone().requires_grad_(True)
+        if kind == "copy":
+            t = t0[None].expand(B, -1, -1, -1, -1, -1).contiguous()
+        elif kind == "batch1":
+            t = t0[None]
+        else:
+            t = t0[None].expand(B, -1, -1, -1, -1, -1)
+        v = torch.from_numpy(v_np).to(dev).requires_grad_(True)
+        out = R._run(idx, t, 64, False, 0.1, 100, 1e-3, (0, 0, 0), True, False, False, face_light=light,
+                     textures_fill_back=fill_back, vertices=v)
+        (out[0] * g).sum().backward()
+        res[kind] = (out[0].detach(), t0.grad, v.grad)
+    for kind in ("batch1", "expanded"):
+        assert torch.equal(res[kind][0], res["copy"][0])
+        assert rel_err(res[kind][1].cpu(), res["copy"][1].cpu()) <= 1e-5
+        assert rel_err(res[kind][2].cpu(), res["copy"][2].cpu()) <= 1e-5
+
+
+def test_backward_in_two_parts_with_texture_hook():
+    """NR_BWD_PART_TEXTURES / NR_BWD_PART_FACES: the hook sees the finished texture gradient before the edge scan is
+    enqueued, and the two halves add up to exactly what the single call computes."""
+    import importlib
+    R = importlib.import_module("neural_renderer_b200.rasterize")
+    from neural_renderer_b200 import synthetic
+    dev = torch.device("cuda")
+    faces_np = synthetic.sphere_faces(2, 800, seed=3)
+    tex_np = synthetic.random_textures(2, 800, 2, seed=4)
+    g = torch.randn((2, 3, 64, 64), generator=torch.Generator().manual_seed(1)).to(dev)
+
+    def run():
+        f = torch.from_numpy(faces_np).to(dev).requires_grad_(True)
+        t = torch.from_numpy(tex_np).to(dev).requires_grad_(True)
+        (R._run(f, t, 64, False, 0.1, 100, 1e-4, (0, 0, 0), True, False, False)[0] * g).sum().backward()
+        return f.grad, t.grad
+
+    gf0, gt0 = run()
+    seen = {}
+
+    class Pending:
+        def wait(self):
+            seen["waited"] = True
+
+    def hook(grad_textures):
+        seen["tex"] = grad_textures.clone()  # stream-ordered: the edge scan has not been enqueued yet
+        return Pending()
+
+    prev = R.set_texture_grad_hook(hook)
+    try:
+        gf1, gt1 = run()
+    finally:
+        R.set_texture_grad_hook(prev)
+    assert seen.get("waited") and torch.equal(seen["tex"], gt1)
+    assert rel_err(gt1.cpu(), gt0.cpu()) <= 1e-6
+    assert rel_err(gf1.cpu(), gf0.cpu()) <= 1e-5
+
+
+def test_renderer_fused_path_has_no_face_tensor(teapot):
+    """Renderer.render* with the fused path: gradients reach the vertices through the indexed rasterizer and agree
+    with the op-by-op formulation (vertices_to_faces + lighting + doubled textures)."""
+    import neural_renderer as nr
+    dev = torch.device("cuda")
+    v, f = teapot
+    B = 2
+    faces_idx = torch.from_numpy(np.stack([f] * B)).to(dev)
+    tex0 = torch.rand((B, f.shape[0], 2, 2, 2, 3), generator=torch.Generator().manual_seed(1)).to(dev)
+    out = {}
+    for fused in (True, False):
+        vert = torch.from_numpy(np.stack([v, v * 0.9])).to(dev).requires_grad_(True)
+        tex = tex0.clone().requires_grad_(True)
+        r = nr.Renderer()
+        r.fused = fused
+        r.image_size = 64
+        r.eye = nr.get_points_from_angles(2.732, 20, 50)
+        imgs = (r.render(vert, faces_idx, tex), r.render_silhouettes(vert, faces_idx), r.render_depth(vert, faces_idx))
+        gen = torch.Generator().manual_seed(7)
+        loss = sum((im * torch.randn(im.shape, generator=gen).to(dev)).sum() for im in imgs)
+        loss.backward()
+        out[fused] = (imgs, vert.grad, tex.grad)
+    for a, b in zip(out[True][0], out[False][0]):
+        assert rel_err(a.detach().cpu(), b.detach().cpu()) <= 1e-5
+    assert rel_err(out[True][1].cpu(), out[False][1].cpu()) <= 1e-4
+    assert rel_err(out[True][2].cpu(), out[False][2].cpu()) <= 1e-4
