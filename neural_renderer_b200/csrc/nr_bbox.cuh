@@ -22,6 +22,24 @@ __device__ __forceinline__ int unpack_lo(uint32_t v) { return (int)(short)(v & 0
 __device__ __forceinline__ int unpack_hi(uint32_t v) { return (int)(short)(v >> 16); }
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 
+// Conservative pixel box of a face; false = the face can never win a pixel (back-facing, rasterize.py:252/:306/:540, a
+// non-finite x/y, or entirely off screen).
+__device__ __forceinline__ bool face_pixel_box(float x0, float y0, float x1, float y1, float x2, float y2, int S, int& xlo,
+                                               int& xhi, int& ylo, int& yhi) {
+    const bool finite = isfinite(x0) && isfinite(y0) && isfinite(x1) && isfinite(y1) && isfinite(x2) && isfinite(y2);
+    if (!finite || nr::backside(x0, y0, x1, y1, x2, y2)) return false;
+    const float fS = (float)S;
+    // to_pixel is monotone in its argument, so the box of the pixel-space vertices is the image of the box
+    const float pxmin = nr::to_pixel(fminf(x0, fminf(x1, x2)), fS), pxmax = nr::to_pixel(fmaxf(x0, fmaxf(x1, x2)), fS);
+    const float pymin = nr::to_pixel(fminf(y0, fminf(y1, y2)), fS), pymax = nr::to_pixel(fmaxf(y0, fmaxf(y1, y2)), fS);
+    const float lim = (float)(S - 1);
+    const float fx0 = fmaxf(floorf(pxmin - kBoxMargin), 0.0f), fx1 = fminf(ceilf(pxmax + kBoxMargin), lim);
+    const float fy0 = fmaxf(floorf(pymin - kBoxMargin), 0.0f), fy1 = fminf(ceilf(pymax + kBoxMargin), lim);
+    if (!(fx0 <= fx1 && fy0 <= fy1)) return false;
+    xlo = (int)fx0; xhi = (int)fx1; ylo = (int)fy0; yhi = (int)fy1;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------ k_face_bbox
 __global__ void __launch_bounds__(kChunk) k_face_bbox(const nr::FaceSrc src, int F, int S, int ngroups,
                                                       uint2* __restrict__ bbox, uint2* __restrict__ group_bbox) {
@@ -31,19 +49,8 @@ __global__ void __launch_bounds__(kChunk) k_face_bbox(const nr::FaceSrc src, int
     if (f < F) {
         const float *v0 = nr::face_vertex(src, b, f, 0), *v1 = nr::face_vertex(src, b, f, 1), *v2 = nr::face_vertex(src, b, f, 2);
         const float x0 = __ldg(v0), y0 = __ldg(v0 + 1), x1 = __ldg(v1), y1 = __ldg(v1 + 1), x2 = __ldg(v2), y2 = __ldg(v2 + 1);
-        const bool finite = isfinite(x0) && isfinite(y0) && isfinite(x1) && isfinite(y1) && isfinite(x2) && isfinite(y2);
-        if (finite && !nr::backside(x0, y0, x1, y1, x2, y2)) {
-            const float fS = (float)S;
-            // to_pixel is monotone in its argument, so the box of the pixel-space vertices is the image of the box
-            const float pxmin = nr::to_pixel(fminf(x0, fminf(x1, x2)), fS), pxmax = nr::to_pixel(fmaxf(x0, fmaxf(x1, x2)), fS);
-            const float pymin = nr::to_pixel(fminf(y0, fminf(y1, y2)), fS), pymax = nr::to_pixel(fmaxf(y0, fmaxf(y1, y2)), fS);
-            const float lim = (float)(S - 1);
-            const float fx0 = fmaxf(floorf(pxmin - kBoxMargin), 0.0f), fx1 = fminf(ceilf(pxmax + kBoxMargin), lim);
-            const float fy0 = fmaxf(floorf(pymin - kBoxMargin), 0.0f), fy1 = fminf(ceilf(pymax + kBoxMargin), lim);
-            if (fx0 <= fx1 && fy0 <= fy1) {
-                xlo = (int)fx0; xhi = (int)fx1; ylo = (int)fy0; yhi = (int)fy1;
-            }
-        }
+        int bx0, bx1, by0, by1;
+        if (face_pixel_box(x0, y0, x1, y1, x2, y2, S, bx0, bx1, by0, by1)) { xlo = bx0; xhi = bx1; ylo = by0; yhi = by1; }
         bbox[(size_t)b * F + f] = make_uint2(pack16(xlo, xhi), pack16(ylo, yhi));
     }
     // union box of the warp's 32 faces (empty faces do not contribute; an all-empty group gets an empty box)
