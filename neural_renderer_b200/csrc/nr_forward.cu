@@ -35,6 +35,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "nr_b200.h"
 #include "nr_math.cuh"
 #include "nr_internal.h"
@@ -47,6 +49,7 @@ constexpr int kXpTable = 2048;         // pixel-centre table in shared memory fo
 constexpr int kBigArea = 1024;         // faces whose (clipped) pixel box is larger go through k_raster_big
 constexpr int kBigTile = 64;           // screen tile of k_raster_big
 constexpr int kRecWords = 12;          // {inv[9], z0, z1, z2}
+constexpr uint32_t kStageBytes = 32 * 1024;  // shared memory of a k_resolve CTA for staged texture cubes
 
 struct FwdParams {
     nr::FaceSrc src;
@@ -57,6 +60,8 @@ struct FwdParams {
     unsigned long long* zbuf;  // [B,S,S] raster orientation (row = yi): ordered zp << 32 | face index, ~0 = empty
     float4* tab;               // [B,F,3] float4: {inv0..3}, {inv4..7}, {inv8, z0, z1, z2} of every drawn face
     int* big_cnt;              // [B] number of big faces - 1 (memset to 0xFF = -1)
+    int* work_next;            // next (item, group) unit of k_raster_faces - 1 (memset to -1)
+    int* any_big;              // -1 until some item has a big face
     int* big_list;             // [B,F]
     int32_t* fim;
     float* wmap;
@@ -189,7 +194,6 @@ __global__ void __launch_bounds__(kFaceWarps * 32) k_raster_faces(const __grid_c
     WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw);
     float* centres = reinterpret_cast<float*>(smem_raw + sizeof(WarpScratch) * kFaceWarps);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y;
     const int S = p.S;
     const bool use_table = S <= kXpTable;
     if (use_table) {
@@ -197,55 +201,63 @@ __global__ void __launch_bounds__(kFaceWarps * 32) k_raster_faces(const __grid_c
         __syncthreads();
     }
     const PixelCentres pc{use_table ? centres : nullptr, S, (float)S};
-    const int g = blockIdx.x * kFaceWarps + warp;
-    if (g >= p.ngroups) return;
     WarpScratch& ws = scratch[warp];
-    const int f = (g << 5) + lane;
-    int h = 0;
-    if (f < p.F) {
-        float c[9];
-        nr::load_face(p.src, b, f, c);
-        int xlo, xhi, ylo, yhi;
-        if (face_pixel_box(c[0], c[1], c[3], c[4], c[6], c[7], S, xlo, xhi, ylo, yhi)) {
-            const float fS = (float)S;
-            float inv[9];
-            nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS), nr::to_pixel(c[4], fS),
-                             nr::to_pixel(c[6], fS), nr::to_pixel(c[7], fS), inv);
-            const float4 t0 = make_float4(inv[0], inv[1], inv[2], inv[3]), t1 = make_float4(inv[4], inv[5], inv[6], inv[7]),
-                         t2 = make_float4(inv[8], c[2], c[5], c[8]);
-            float4* gt = p.tab + ((size_t)b * p.F + f) * 3;
-            gt[0] = t0; gt[1] = t1; gt[2] = t2;
-            if ((xhi - xlo + 1) * (yhi - ylo + 1) > kBigArea) {
-                const int slot = atomicAdd(p.big_cnt + b, 1) + 1;  // counters start at -1
-                p.big_list[(size_t)b * p.F + slot] = f;
-            } else {
-                h = yhi - ylo + 1;
-                ws.tab[lane][0] = t0; ws.tab[lane][1] = t1; ws.tab[lane][2] = t2;
-                ws.rec[lane][0] = make_float4(c[0], c[1], c[3], c[4]);
-                ws.rec[lane][1] = make_float4(c[6], c[7], __uint_as_float((uint32_t)xlo | ((uint32_t)xhi << 16)),
-                                              __uint_as_float((uint32_t)ylo | ((uint32_t)yhi << 16)));
+    // Persistent warps pull (item, group) units from one counter: groups differ a lot in cost (all back faces: nothing;
+    // a dense front patch: thousands of fragments), so a static assignment leaves most of the chip idle in the tail.
+    const int nunits = p.B * p.ngroups;
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(p.work_next, 1) + 1;  // the counter starts at -1
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= nunits) break;
+        const int b = u / p.ngroups, g = u - b * p.ngroups;
+        const int f = (g << 5) + lane;
+        int h = 0;
+        if (f < p.F) {
+            float c[9];
+            nr::load_face(p.src, b, f, c);
+            int xlo, xhi, ylo, yhi;
+            if (face_pixel_box(c[0], c[1], c[3], c[4], c[6], c[7], S, xlo, xhi, ylo, yhi)) {
+                const float fS = (float)S;
+                float inv[9];
+                nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS), nr::to_pixel(c[4], fS),
+                                 nr::to_pixel(c[6], fS), nr::to_pixel(c[7], fS), inv);
+                const float4 t0 = make_float4(inv[0], inv[1], inv[2], inv[3]), t1 = make_float4(inv[4], inv[5], inv[6], inv[7]),
+                             t2 = make_float4(inv[8], c[2], c[5], c[8]);
+                float4* gt = p.tab + ((size_t)b * p.F + f) * 3;
+                gt[0] = t0; gt[1] = t1; gt[2] = t2;
+                if ((xhi - xlo + 1) * (yhi - ylo + 1) > kBigArea) {
+                    const int slot = atomicAdd(p.big_cnt + b, 1) + 1;  // counters start at -1
+                    p.big_list[(size_t)b * p.F + slot] = f;
+                    if (slot == 0) *p.any_big = 0;
+                } else {
+                    h = yhi - ylo + 1;
+                    ws.tab[lane][0] = t0; ws.tab[lane][1] = t1; ws.tab[lane][2] = t2;
+                    ws.rec[lane][0] = make_float4(c[0], c[1], c[3], c[4]);
+                    ws.rec[lane][1] = make_float4(c[6], c[7], __uint_as_float((uint32_t)xlo | ((uint32_t)xhi << 16)),
+                                                  __uint_as_float((uint32_t)ylo | ((uint32_t)yhi << 16)));
+                }
             }
         }
-    }
-    int incl = h;
+        int incl = h;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int nrows = __shfl_sync(0xffffffffu, incl, 31);
+        if (nrows == 0) continue;
+        ws.rowpre[lane] = incl - h;
+        __syncwarp();
+        raster_rows(p, ws, pc, b, nrows, g << 5, lane);
+        __syncwarp();  // the scratch is rewritten by the next unit
     }
-    const int nrows = __shfl_sync(0xffffffffu, incl, 31);
-    if (nrows == 0) return;
-    ws.rowpre[lane] = incl - h;
-    __syncwarp();
-    raster_rows(p, ws, pc, b, nrows, g << 5, lane);
 }
 
 // -------------------------------------------------------------------------------------------- k_raster_big
 //@phase k_raster_big
 __global__ void __launch_bounds__(256) k_raster_big(const __grid_constant__ FwdParams p) {
-    const int b = blockIdx.y;
-    const int nbig = __ldg(p.big_cnt + b) + 1;
-    if (nbig <= 0) return;
+    if (__ldg(p.any_big) < 0) return;  // no item has a big face: the common case costs one load
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw);
     float* centres = reinterpret_cast<float*>(smem_raw + sizeof(WarpScratch) * 8);
@@ -258,30 +270,36 @@ __global__ void __launch_bounds__(256) k_raster_big(const __grid_constant__ FwdP
     }
     const PixelCentres pc{use_table ? centres : nullptr, S, (float)S};
     const int tiles_x = (S + kBigTile - 1) / kBigTile;
-    const int tx0 = (blockIdx.x % tiles_x) * kBigTile, ty0 = (blockIdx.x / tiles_x) * kBigTile;
-    const int tx1 = min(tx0 + kBigTile, S) - 1, ty1 = min(ty0 + kBigTile, S) - 1;
+    const int ntiles = tiles_x * tiles_x;
     WarpScratch& ws = scratch[warp];
-    for (int i = warp; i < nbig; i += 8) {
-        const int f = __ldg(p.big_list + (size_t)b * p.F + i);
-        float c[9];
-        nr::load_face(p.src, b, f, c);  // warp-uniform
-        int xlo, xhi, ylo, yhi;
-        if (!face_pixel_box(c[0], c[1], c[3], c[4], c[6], c[7], S, xlo, xhi, ylo, yhi)) continue;
-        xlo = max(xlo, tx0); xhi = min(xhi, tx1); ylo = max(ylo, ty0); yhi = min(yhi, ty1);
-        if (xlo > xhi || ylo > yhi) continue;
-        // the face sits in slot 0 of the warp's scratch; every lane rasterizes rows of that one face
-        if (lane == 0) {
-            const float4* gt = p.tab + ((size_t)b * p.F + f) * 3;
-            ws.tab[0][0] = gt[0]; ws.tab[0][1] = gt[1]; ws.tab[0][2] = gt[2];
-            ws.rec[0][0] = make_float4(c[0], c[1], c[3], c[4]);
-            ws.rec[0][1] = make_float4(c[6], c[7], __uint_as_float((uint32_t)xlo | ((uint32_t)xhi << 16)),
-                                       __uint_as_float((uint32_t)ylo | ((uint32_t)yhi << 16)));
+    for (int unit = blockIdx.x; unit < ntiles * p.B; unit += gridDim.x) {
+        const int b = unit / ntiles, tile = unit - b * ntiles;
+        const int nbig = __ldg(p.big_cnt + b) + 1;
+        if (nbig <= 0) continue;
+        const int tx0 = (tile % tiles_x) * kBigTile, ty0 = (tile / tiles_x) * kBigTile;
+        const int tx1 = min(tx0 + kBigTile, S) - 1, ty1 = min(ty0 + kBigTile, S) - 1;
+        for (int i = warp; i < nbig; i += 8) {
+            const int f = __ldg(p.big_list + (size_t)b * p.F + i);
+            float c[9];
+            nr::load_face(p.src, b, f, c);  // warp-uniform
+            int xlo, xhi, ylo, yhi;
+            if (!face_pixel_box(c[0], c[1], c[3], c[4], c[6], c[7], S, xlo, xhi, ylo, yhi)) continue;
+            xlo = max(xlo, tx0); xhi = min(xhi, tx1); ylo = max(ylo, ty0); yhi = min(yhi, ty1);
+            if (xlo > xhi || ylo > yhi) continue;
+            // the face sits in slot 0 of the warp's scratch; every lane rasterizes rows of that one face
+            if (lane == 0) {
+                const float4* gt = p.tab + ((size_t)b * p.F + f) * 3;
+                ws.tab[0][0] = gt[0]; ws.tab[0][1] = gt[1]; ws.tab[0][2] = gt[2];
+                ws.rec[0][0] = make_float4(c[0], c[1], c[3], c[4]);
+                ws.rec[0][1] = make_float4(c[6], c[7], __uint_as_float((uint32_t)xlo | ((uint32_t)xhi << 16)),
+                                           __uint_as_float((uint32_t)ylo | ((uint32_t)yhi << 16)));
+            }
+            const int h = yhi - ylo + 1;
+            ws.rowpre[lane] = lane == 0 ? 0 : h;  // lane 0 owns rows [0, h); the other prefix entries lie past the end
+            __syncwarp();
+            raster_rows(p, ws, pc, b, h, f, lane);  // face_base + slot 0 = f
+            __syncwarp();
         }
-        const int h = yhi - ylo + 1;
-        ws.rowpre[lane] = lane == 0 ? 0 : h;  // lane 0 owns rows [0, h); the other prefix entries lie past the end
-        __syncwarp();
-        raster_rows(p, ws, pc, b, h, f, lane);  // face_base + slot 0 = f
-        __syncwarp();
     }
 }
 
@@ -292,6 +310,88 @@ struct Shaded {
     float w0, w1, w2, depth, r, g, b, alpha;
 };
 
+// ---- bulk asynchronous copies (TMA engine, cp.async.bulk -> SASS UBLKCP) completing on a shared-memory mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+
+// geometry half of a pixel: winner's record -> weights (+ texture coordinates when drawing RGB)
+struct PixelGeom {
+    int fn, cube;
+    bool rev;
+    float zp, w[3];
+};
+
+template <bool kLit>
+__device__ __forceinline__ void blend_corners(const FwdParams& p, const nr::TexCoord& tc, const float* tex, bool rev, int b, int fn,
+                                              float& r, float& g, float& bl) {
+    const int ts = p.ts;
+    float l0 = 1.0f, l1 = 1.0f, l2 = 1.0f;
+    if (kLit) {
+        const float* lp = p.face_light + ((size_t)b * p.F + fn) * 3;
+        l0 = __ldg(lp); l1 = __ldg(lp + 1); l2 = __ldg(lp + 2);
+    }
+    r = g = bl = 0.0f;
+#pragma unroll
+    for (int pn = 0; pn < 8; pn++) {
+        const float cw = nr::corner_weight(tc, pn);
+        const float* t = tex + (rev ? nr::corner_index_rev(tc, pn, ts) : nr::corner_index(tc, pn, ts)) * 3;
+        float t0 = t[0], t1 = t[1], t2 = t[2];
+        if (kLit) {  // lighting.py:52 texel * light, rounded like the materialised product
+            t0 = __fmul_rn(t0, l0); t1 = __fmul_rn(t1, l1); t2 = __fmul_rn(t2, l2);
+        }
+        r = __fmaf_rn(cw, t0, r);
+        g = __fmaf_rn(cw, t1, g);
+        bl = __fmaf_rn(cw, t2, bl);
+    }
+}
+
+// rasterize.py:389 -- the sampler's vertex depths come from batch item 0 (NR_TEX_Z_BATCH0), else from the winner's record
+__device__ __forceinline__ void sampler_depths(const FwdParams& p, int fn, const float4& cc, float& z0, float& z1, float& z2) {
+    z0 = cc.y; z1 = cc.z; z2 = cc.w;
+    if (p.flags & NR_TEX_Z_BATCH0) {
+        if (p.src.idx == nullptr) {
+            const float* v0 = p.src.faces + (size_t)fn * 9;
+            z0 = __ldg(v0 + 2); z1 = __ldg(v0 + 5); z2 = __ldg(v0 + 8);
+        } else {
+            z0 = __ldg(nr::face_vertex(p.src, 0, fn, 0) + 2);
+            z1 = __ldg(nr::face_vertex(p.src, 0, fn, 1) + 2);
+            z2 = __ldg(nr::face_vertex(p.src, 0, fn, 2) + 2);
+        }
+    }
+}
+
+// cube of face fn (NR_TEX_FILL_BACK: the reversed copy of face f - F/2 samples that face's cube with reversed axes)
+__device__ __forceinline__ int face_cube(const FwdParams& p, int fn, bool& rev) {
+    rev = false;
+    if (p.flags & NR_TEX_FILL_BACK) {
+        const int ncubes = p.F >> 1;
+        if (fn >= ncubes) { rev = true; return fn - ncubes; }
+    }
+    return fn;
+}
+
+// one pixel, every texel straight from global memory (anti-aliased quads, texture sizes the bulk copy cannot stage)
+template <bool kLit>
 __device__ __forceinline__ Shaded shade_pixel(const FwdParams& p, int b, unsigned long long key, int xi, int yi, float bgr,
                                               float bgg, float bgb) {
     Shaded o;
@@ -309,107 +409,149 @@ __device__ __forceinline__ Shaded shade_pixel(const FwdParams& p, int b, unsigne
     o.fim = fn; o.w0 = w[0]; o.w1 = w[1]; o.w2 = w[2]; o.depth = zp; o.alpha = 1.0f;
     o.r = o.g = o.b = 0.0f;
     if (p.flags & NR_RETURN_RGB) {
-        float z0 = cc.y, z1 = cc.z, z2 = cc.w;
-        if (p.flags & NR_TEX_Z_BATCH0) {  // rasterize.py:389 -- vertex depths of batch item 0
-            z0 = __ldg(nr::face_vertex(p.src, 0, fn, 0) + 2);
-            z1 = __ldg(nr::face_vertex(p.src, 0, fn, 1) + 2);
-            z2 = __ldg(nr::face_vertex(p.src, 0, fn, 2) + 2);
-        }
+        float z0, z1, z2;
+        sampler_depths(p, fn, cc, z0, z1, z2);
         const int ts = p.ts;
         const nr::TexCoord tc = nr::texture_coords(w, zp, z0, z1, z2, ts, p.tex_cmp, p.tex_val);
-        // NR_TEX_FILL_BACK: the reversed copy of face f - F/2 samples that face's cube with reversed axes
-        int cube = fn;
-        bool rev = false;
-        if (p.flags & NR_TEX_FILL_BACK) {
-            const int ncubes = p.F >> 1;
-            if (fn >= ncubes) { cube = fn - ncubes; rev = true; }
-        }
+        bool rev;
+        const int cube = face_cube(p, fn, rev);
         const float* tex = p.textures + ((size_t)b * p.tex_bstride + cube) * (size_t)(ts * ts * ts) * 3;
-        float l0 = 1.0f, l1 = 1.0f, l2 = 1.0f;
-        const bool lit = p.face_light != nullptr;
-        if (lit) {
-            const float* lp = p.face_light + ((size_t)b * p.F + fn) * 3;
-            l0 = __ldg(lp); l1 = __ldg(lp + 1); l2 = __ldg(lp + 2);
-        }
-        float r = 0.0f, g = 0.0f, bl = 0.0f;
-#pragma unroll
-        for (int pn = 0; pn < 8; pn++) {
-            const float cw = nr::corner_weight(tc, pn);
-            const float* t = tex + (rev ? nr::corner_index_rev(tc, pn, ts) : nr::corner_index(tc, pn, ts)) * 3;
-            float t0 = __ldg(t + 0), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
-            if (lit) {  // lighting.py:52 texel * light, rounded like the materialised product
-                t0 = __fmul_rn(t0, l0); t1 = __fmul_rn(t1, l1); t2 = __fmul_rn(t2, l2);
-            }
-            r = __fmaf_rn(cw, t0, r);
-            g = __fmaf_rn(cw, t1, g);
-            bl = __fmaf_rn(cw, t2, bl);
-        }
-        o.r = r; o.g = g; o.b = bl;
+        blend_corners<kLit>(p, tc, tex, rev, b, fn, o.r, o.g, o.b);
     }
     return o;
 }
 
 //@phase resolve + stores
-template <bool kAA>
-__global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ FwdParams p) {
-    const int b = blockIdx.y;
+// grid = (column chunks, API rows, batch items): row / item are block-uniform, all offsets are 32-bit.
+//
+// kStage (RGB, no anti-aliasing, cube size a multiple of 16 bytes): the CTA = 256 consecutive pixels of one image row.
+// Runs of neighbouring pixels that show the same texture cube are found with a ballot; the first pixel of every run
+// issues ONE asynchronous bulk copy (cp.async.bulk, the TMA engine) of that face's whole ts^3 cube into shared memory,
+// all copies of the CTA complete on one mbarrier, and while they are in flight every thread reads its winner's record
+// and evaluates weights and texture coordinates.  The 24 texel reads of the trilinear blend then hit shared memory
+// instead of being 24 dependent, uncoalesced global loads behind the record load.  Runs beyond the staging capacity
+// (and the other kernel variants) sample global memory directly.
+template <bool kAA, bool kStage, bool kLit>
+__global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ FwdParams p, int nslots) {
+    extern __shared__ __align__(16) unsigned char stage_raw[];
+    __shared__ uint64_t s_bar;
+    __shared__ int s_runs[8];
+    const int b = blockIdx.z;
     const int S = p.S;
-    const size_t plane = (size_t)S * S;
+    const uint32_t plane = (uint32_t)S * (uint32_t)S;
     float bgr = p.bg[0], bgg = p.bg[1], bgb = p.bg[2];
     if (p.flags & NR_BG_PER_BATCH) {
         bgr = __ldg(p.bg_batch + 3 * b + 0); bgg = __ldg(p.bg_batch + 3 * b + 1); bgb = __ldg(p.bg_batch + 3 * b + 2);
     }
     const bool want_rgb = (p.flags & NR_RETURN_RGB) != 0;
     const unsigned long long* zb = p.zbuf + (size_t)b * plane;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (!kAA) {
-        // thread = one pixel of the IMAGE (row 0 = top): raster row yi = S - 1 - row
-        if (i >= plane) return;
-        const int row = (int)(i / S), xi = (int)(i - (size_t)row * S);
-        const int yi = S - 1 - row;
-        const Shaded s = shade_pixel(p, b, __ldg(zb + (size_t)yi * S + xi), xi, yi, bgr, bgg, bgb);
-        const size_t o = (size_t)b * plane + i;
-        p.fim[o] = s.fim;
-        p.dmap[o] = s.depth;
-        float* wm = p.wmap + (size_t)b * 3 * plane + i;
-        wm[0] = s.w0; wm[plane] = s.w1; wm[2 * plane] = s.w2;
-        if (p.alpha) p.alpha[o] = s.alpha;
-        if (want_rgb) {
-            float* rm = p.rgb + (size_t)b * 3 * plane + i;
-            rm[0] = s.r; rm[plane] = s.g; rm[2 * plane] = s.b;
+    int32_t* fim = p.fim + (size_t)b * plane;
+    float* dmap = p.dmap + (size_t)b * plane;
+    float* wmap = p.wmap + (size_t)b * 3 * plane;
+    float* rgb = want_rgb ? p.rgb + (size_t)b * 3 * plane : nullptr;
+    float* alpha = p.alpha ? p.alpha + (size_t)b * plane : nullptr;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!kAA && kStage) {
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        const int row = blockIdx.y, yi = S - 1 - row;
+        if (tid == 0) mbar_init(&s_bar, 1);
+        const unsigned long long key = col < S ? __ldg(zb + (uint32_t)yi * S + col) : ~0ull;
+        const bool covered = key != ~0ull;
+        const int fn = (int)(uint32_t)(key & 0xFFFFFFFFull);
+        bool rev = false;
+        const int cube = covered ? face_cube(p, fn, rev) : -1;
+        const int left = __shfl_up_sync(0xffffffffu, cube, 1);
+        const bool head = covered && (lane == 0 || cube != left);
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) s_runs[warp] = __popc(heads);
+        __syncthreads();
+        int base = 0, total = 0;
+        const int nwarps = blockDim.x >> 5;
+        for (int w = 0; w < nwarps; w++) {
+            const int c = s_runs[w];
+            if (w < warp) base += c;
+            total += c;
         }
+        const int ts = p.ts;
+        const uint32_t cube_bytes = (uint32_t)(ts * ts * ts) * 12u;
+        const int slot = base + __popc(heads & ((2u << lane) - 1u)) - 1;  // run of this pixel (2u << 31 wraps: all heads)
+        const bool staged = covered && slot < nslots;
+        if (tid == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)min(total, nslots) * cube_bytes);
+        const float* gtex = p.textures + ((size_t)b * p.tex_bstride + (covered ? cube : 0)) * (size_t)(ts * ts * ts) * 3;
+        float* stex = reinterpret_cast<float*>(stage_raw) + (size_t)(staged ? slot : 0) * (cube_bytes >> 2);
+        if (head && staged) bulk_copy_g2s(stex, gtex, cube_bytes, &s_bar);
+        if (col >= S) return;
+        const uint32_t o = (uint32_t)row * S + col;
+        if (!covered) {
+            fim[o] = -1;
+            dmap[o] = p.far_val;
+            wmap[o] = 0.0f; wmap[o + plane] = 0.0f; wmap[o + 2 * plane] = 0.0f;
+            if (alpha) alpha[o] = 0.0f;
+            rgb[o] = bgr; rgb[o + plane] = bgg; rgb[o + 2 * plane] = bgb;
+            return;
+        }
+        // while the cubes are in flight: record -> weights -> texture coordinates
+        const float zp = nr::ordered_to_float((uint32_t)(key >> 32));
+        const float4* t4 = p.tab + ((size_t)b * p.F + fn) * 3;
+        const float4 a = __ldg(t4), bb = __ldg(t4 + 1), cc = __ldg(t4 + 2);
+        const float inv[9] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w, cc.x};
+        float w[3];
+        nr::barycentric_weights(inv, (float)col, (float)yi, w);
+        float z0, z1, z2;
+        sampler_depths(p, fn, cc, z0, z1, z2);
+        const nr::TexCoord tc = nr::texture_coords(w, zp, z0, z1, z2, ts, p.tex_cmp, p.tex_val);
+        fim[o] = fn;
+        dmap[o] = zp;
+        wmap[o] = w[0]; wmap[o + plane] = w[1]; wmap[o + 2 * plane] = w[2];
+        if (alpha) alpha[o] = 1.0f;
+        float r, g, bl;
+        if (staged) {
+            mbar_wait(&s_bar, 0);
+            blend_corners<kLit>(p, tc, stex, rev, b, fn, r, g, bl);
+        } else {
+            blend_corners<kLit>(p, tc, gtex, rev, b, fn, r, g, bl);
+        }
+        rgb[o] = r; rgb[o + plane] = g; rgb[o + 2 * plane] = bl;
+    } else if (!kAA) {
+        // thread = one pixel of the IMAGE (row 0 = top): raster row yi = S - 1 - row
+        if (col >= S) return;
+        const int row = blockIdx.y, yi = S - 1 - row;
+        const Shaded s = shade_pixel<kLit>(p, b, __ldg(zb + (uint32_t)yi * S + col), col, yi, bgr, bgg, bgb);
+        const uint32_t o = (uint32_t)row * S + col;
+        fim[o] = s.fim;
+        dmap[o] = s.depth;
+        wmap[o] = s.w0; wmap[o + plane] = s.w1; wmap[o + 2 * plane] = s.w2;
+        if (alpha) alpha[o] = s.alpha;
+        if (want_rgb) { rgb[o] = s.r; rgb[o + plane] = s.g; rgb[o + 2 * plane] = s.b; }
     } else {
         // thread = one pooled API pixel = one 2x2 quad of the raster
         const int H = S >> 1;
-        const size_t oplane = (size_t)H * H;
-        if (i >= oplane) return;
-        const int orow = (int)(i / H), ocol = (int)(i - (size_t)orow * H);
+        const uint32_t oplane = (uint32_t)H * (uint32_t)H;
+        if (col >= H) return;
+        const int orow = blockIdx.y;
         float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f, sd = 0.f;
         // the four pixels are shaded one after the other (keeps the register footprint of a single pixel) in image
         // order: top-left, top-right, bottom-left, bottom-right
 #pragma unroll 1
         for (int k = 0; k < 4; k++) {
-            const int row = 2 * orow + (k >> 1), xi = 2 * ocol + (k & 1);
+            const int row = 2 * orow + (k >> 1), xi = 2 * col + (k & 1);
             const int yi = S - 1 - row;
-            const Shaded s = shade_pixel(p, b, __ldg(zb + (size_t)yi * S + xi), xi, yi, bgr, bgg, bgb);
-            const size_t o = (size_t)b * plane + (size_t)row * S + xi;
-            p.fim[o] = s.fim;
-            p.dmap[o] = s.depth;
-            float* wm = p.wmap + (size_t)b * 3 * plane + (size_t)row * S + xi;
-            wm[0] = s.w0; wm[plane] = s.w1; wm[2 * plane] = s.w2;
-            if (p.alpha) p.alpha[o] = s.alpha;
-            if (want_rgb) {
-                float* rm = p.rgb + (size_t)b * 3 * plane + (size_t)row * S + xi;
-                rm[0] = s.r; rm[plane] = s.g; rm[2 * plane] = s.b;
-            }
+            const Shaded s = shade_pixel<kLit>(p, b, __ldg(zb + (uint32_t)yi * S + xi), xi, yi, bgr, bgg, bgb);
+            const uint32_t o = (uint32_t)row * S + xi;
+            fim[o] = s.fim;
+            dmap[o] = s.depth;
+            wmap[o] = s.w0; wmap[o + plane] = s.w1; wmap[o + 2 * plane] = s.w2;
+            if (alpha) alpha[o] = s.alpha;
+            if (want_rgb) { rgb[o] = s.r; rgb[o + plane] = s.g; rgb[o + 2 * plane] = s.b; }
             sr += s.r; sg += s.g; sb += s.b; sa += s.alpha; sd += s.depth;
         }
+        const uint32_t oo = (uint32_t)orow * H + col;
         if (want_rgb && p.out_rgb) {
-            float* orgb = p.out_rgb + (size_t)b * 3 * oplane + i;
+            float* orgb = p.out_rgb + (size_t)b * 3 * oplane + oo;
             orgb[0] = sr * 0.25f; orgb[oplane] = sg * 0.25f; orgb[2 * oplane] = sb * 0.25f;
         }
-        if (p.out_alpha) p.out_alpha[(size_t)b * oplane + i] = sa * 0.25f;
-        if (p.out_depth) p.out_depth[(size_t)b * oplane + i] = sd * 0.25f;
+        if (p.out_alpha) p.out_alpha[(size_t)b * oplane + oo] = sa * 0.25f;
+        if (p.out_depth) p.out_depth[(size_t)b * oplane + oo] = sd * 0.25f;
     }
 }
 
@@ -430,8 +572,8 @@ struct FwdLayout {
 // workspace = big-face counters | z-buffer (one memset covers both) | face records | big-face lists
 FwdLayout fwd_layout(int B, int F, int S) {
     FwdLayout L{};
-    L.off_cnt = 0;
-    L.off_zbuf = nr_align_up((size_t)B * sizeof(int), 256);
+    L.off_cnt = 0;  // [B] big-face counters, then work_next, any_big
+    L.off_zbuf = nr_align_up((size_t)(B + 2) * sizeof(int), 256);
     L.off_tab = L.off_zbuf + nr_align_up((size_t)B * S * S * sizeof(unsigned long long), 256);
     L.off_list = L.off_tab + nr_align_up((size_t)B * F * kRecWords * sizeof(float), 256);
     L.total = L.off_list + nr_align_up((size_t)B * F * sizeof(int), 256);
@@ -462,7 +604,7 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
         if ((flags & NR_BG_PER_BATCH) && !a->background_batch) return NR_ERR_INVALID_ARG;
     }
     if ((flags & NR_ANTI_ALIASING) && (S & 1)) return NR_ERR_INVALID_ARG;
-    if (S > 32767 || B > 65535) return NR_ERR_UNSUPPORTED;
+    if (S > 32767 || B > 65535) return NR_ERR_UNSUPPORTED;  // 32-bit pixel offsets; batch = grid.z of the resolve pass
     const size_t need = nr_b200_forward_workspace_bytes(B, F, S, ts, flags);
     if (!a->workspace || a->workspace_bytes < need || ((uintptr_t)a->workspace & 15)) return NR_ERR_WORKSPACE;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
@@ -475,6 +617,8 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
     p.textures = a->textures; p.bg_batch = a->background_batch;
     p.face_light = (flags & NR_RETURN_RGB) ? a->face_light : nullptr;
     p.big_cnt = (int*)(wsb + L.off_cnt);
+    p.work_next = p.big_cnt + B;
+    p.any_big = p.big_cnt + B + 1;
     p.zbuf = (unsigned long long*)(wsb + L.off_zbuf);
     p.tab = (float4*)(wsb + L.off_tab);
     p.big_list = (int*)(wsb + L.off_list);
@@ -496,30 +640,58 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
         nr_internal::prof_end(stream);
     }
     const size_t centres_bytes = S <= kXpTable ? (size_t)S * sizeof(float) : 0;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return NR_ERR_CUDA;
     {
         const size_t smem = sizeof(WarpScratch) * kFaceWarps + centres_bytes;
         static nr_internal::SmemOptIn optin;
         if (optin.ensure(k_raster_faces, smem) != cudaSuccess) return NR_ERR_CUDA;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raster_faces, kFaceWarps * 32, smem) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        const long long nunits = (long long)B * p.ngroups;
+        const int grid = (int)std::min<long long>((nunits + kFaceWarps - 1) / kFaceWarps, (long long)sms * per_sm);
         nr_internal::LaunchScope ls("k_raster_faces", stream);
-        k_raster_faces<<<dim3((p.ngroups + kFaceWarps - 1) / kFaceWarps, B), kFaceWarps * 32, smem, stream>>>(p);
+        k_raster_faces<<<grid, kFaceWarps * 32, smem, stream>>>(p);
     }
     {
         const size_t smem = sizeof(WarpScratch) * 8 + centres_bytes;
         static nr_internal::SmemOptIn optin;
         if (optin.ensure(k_raster_big, smem) != cudaSuccess) return NR_ERR_CUDA;
         const int tiles = (S + kBigTile - 1) / kBigTile;
+        const int grid = (int)std::min<long long>((long long)tiles * tiles * B, (long long)sms * 4);
         nr_internal::LaunchScope ls("k_raster_big", stream);
-        k_raster_big<<<dim3(tiles * tiles, B), 256, smem, stream>>>(p);
+        k_raster_big<<<grid, 256, smem, stream>>>(p);
     }
     {
         nr_internal::LaunchScope ls("k_resolve", stream);
-        if (flags & NR_ANTI_ALIASING) {
-            const size_t n = (size_t)(S / 2) * (S / 2);
-            k_resolve<true><<<dim3((unsigned)((n + 255) / 256), B), 256, 0, stream>>>(p);
-        } else {
-            const size_t n = (size_t)S * S;
-            k_resolve<false><<<dim3((unsigned)((n + 255) / 256), B), 256, 0, stream>>>(p);
+        const int width = (flags & NR_ANTI_ALIASING) ? S / 2 : S;   // one thread per API pixel
+        const int bx = width >= 256 ? 256 : ((width + 31) / 32) * 32;
+        const dim3 grid((width + bx - 1) / bx, width, B);
+        // Staging whole cubes with cp.async.bulk needs 16-byte aligned, 16-byte sized cubes; up to kStageBytes of
+        // shared memory per CTA hold the cubes of the row's runs (the rest of the runs read global memory)
+        const bool aa = (flags & NR_ANTI_ALIASING) != 0;
+        const bool lit = p.face_light != nullptr;
+        const uint32_t cube_bytes = (flags & NR_RETURN_RGB) ? (uint32_t)(ts * ts * ts) * 12u : 0u;
+        const bool stage = !aa && (flags & NR_RETURN_RGB) && (cube_bytes % 16u) == 0 && cube_bytes <= kStageBytes / 8 &&
+                           ((uintptr_t)a->textures & 15) == 0;
+        int nslots = 0;
+        size_t smem = 0;
+        if (stage) {
+            nslots = (int)std::min<uint32_t>(kStageBytes / cube_bytes, (uint32_t)bx);
+            smem = (size_t)nslots * cube_bytes;
         }
+#define NR_RESOLVE(AA, ST, LIT)                                                                     \
+    do {                                                                                            \
+        static nr_internal::SmemOptIn optin;                                                        \
+        if (optin.ensure(k_resolve<AA, ST, LIT>, smem) != cudaSuccess) return NR_ERR_CUDA;          \
+        k_resolve<AA, ST, LIT><<<grid, bx, smem, stream>>>(p, nslots);                              \
+    } while (0)
+        if (aa) { if (lit) NR_RESOLVE(true, false, true); else NR_RESOLVE(true, false, false); }
+        else if (stage) { if (lit) NR_RESOLVE(false, true, true); else NR_RESOLVE(false, true, false); }
+        else { if (lit) NR_RESOLVE(false, false, true); else NR_RESOLVE(false, false, false); }
+#undef NR_RESOLVE
     }
     return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
 }
