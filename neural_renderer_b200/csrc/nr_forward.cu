@@ -49,6 +49,7 @@ constexpr int kXpTable = 2048;         // pixel-centre table in shared memory fo
 constexpr int kBigArea = 1024;         // faces whose (clipped) pixel box is larger go through k_raster_big
 constexpr int kBigTile = 64;           // screen tile of k_raster_big
 constexpr int kRecWords = 12;          // {inv[9], z0, z1, z2}
+constexpr int kOwnTable = 256;         // rows / fragments per pass whose owner lane is looked up instead of searched
 constexpr uint32_t kStageBytes = 32 * 1024;  // shared memory of a k_resolve CTA for staged texture cubes
 
 struct FwdParams {
@@ -95,24 +96,32 @@ struct __align__(16) WarpScratch {
     float4 tab[32][3];   // {inv[9], z[3]} of the lane's face
     int rowpre[32];      // first row number of each lane's face
     int spanpre[32];     // first fragment number of each row span of the current pass
+    uint8_t rowown[kOwnTable];   // owner lane of every row of the unit (when there are at most kOwnTable rows)
+    uint8_t fragown[kOwnTable];  // owner lane of every fragment of the current pass (likewise)
 };
 
 //@phase row spans + fragments (shared by k_raster_faces and k_raster_big)
 // Rows `r` in [0, nrows) of this warp's faces are distributed over the lanes (32 per pass).  rowpre[l] = first row of
 // lane l's face (exclusive prefix of the box heights; faces without rows have height 0); face index = face_base + l.
 __device__ __forceinline__ void raster_rows(const FwdParams& p, WarpScratch& ws, const PixelCentres& pc, int b, int nrows,
-                                            int face_base, int lane) {
+                                            int face_base, int lane, bool row_table) {
     unsigned long long* zb = p.zbuf + (size_t)b * p.S * p.S;
     for (int base = 0; base < nrows; base += 32) {
         const int r = base + lane;
         int lo = 1, hi = 0, own = 0, y = 0;
         if (r < nrows) {
-            // owner = last lane whose first row is <= r (upper_bound - 1 over the non-decreasing prefix)
-            int a = 0, bnd = 32;
+            int a;
+            if (row_table) {
+                a = ws.rowown[r];
+            } else {
+                // owner = last lane whose first row is <= r (upper_bound - 1 over the non-decreasing prefix)
+                a = 0;
+                int bnd = 32;
 #pragma unroll
-            for (int it = 0; it < 5; it++) {
-                const int mid = (a + bnd) >> 1;
-                if (ws.rowpre[mid] <= r) a = mid; else bnd = mid;
+                for (int it = 0; it < 5; it++) {
+                    const int mid = (a + bnd) >> 1;
+                    if (ws.rowpre[mid] <= r) a = mid; else bnd = mid;
+                }
             }
             own = a;
             const float4 q0 = ws.rec[a][0], q1 = ws.rec[a][1];
@@ -125,20 +134,26 @@ __device__ __forceinline__ void raster_rows(const FwdParams& p, WarpScratch& ws,
             const float rk[3] = {__fmul_rn(__fsub_rn(yp, y0), __fsub_rn(x1, x0)),
                                  __fmul_rn(__fsub_rn(yp, y1), __fsub_rn(x2, x1)),
                                  __fmul_rn(__fsub_rn(yp, y2), __fsub_rn(x0, x2))};
-            lo = (int)(boxx & 0xFFFFu); hi = (int)(boxx >> 16);
+            const int lo0 = (int)(boxx & 0xFFFFu), hi0 = (int)(boxx >> 16);
+            // out_k(x) = r_k < (xp(x) - x_k) * dy_k is non-decreasing in x for dy_k >= 0 (constant for dy_k == 0) and
+            // non-increasing for dy_k < 0: per edge, the first x where out_k(x) != (dy_k < 0).  The three searches run
+            // over the same interval in lockstep (three independent dependency chains instead of one long one).
+            int a3[3] = {lo0, lo0, lo0}, b3[3] = {hi0 + 1, hi0 + 1, hi0 + 1};
+            const bool neg[3] = {dyk[0] < 0.0f, dyk[1] < 0.0f, dyk[2] < 0.0f};
+            while ((a3[0] < b3[0]) | (a3[1] < b3[1]) | (a3[2] < b3[2])) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if (a3[k] < b3[k]) {
+                        const int mid = (a3[k] + b3[k]) >> 1;
+                        const bool out = rk[k] < __fmul_rn(__fsub_rn(pc(mid), xk[k]), dyk[k]);
+                        if (out != neg[k]) b3[k] = mid; else a3[k] = mid + 1;
+                    }
+                }
+            }
+            lo = lo0; hi = hi0;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                const float xe = xk[k], dy = dyk[k], rr = rk[k];
-                // out(x) = rr < (xp(x) - xe) * dy is non-decreasing in x for dy >= 0 (constant for dy == 0) and
-                // non-increasing for dy < 0: find the first x where out(x) != (dy < 0)
-                const bool neg = dy < 0.0f;
-                int a2 = lo, b2 = hi + 1;
-                while (a2 < b2) {
-                    const int mid = (a2 + b2) >> 1;
-                    const bool out = rr < __fmul_rn(__fsub_rn(pc(mid), xe), dy);
-                    if (out != neg) b2 = mid; else a2 = mid + 1;
-                }
-                if (neg) lo = a2; else hi = a2 - 1;
+                if (neg[k]) lo = max(lo, a3[k]); else hi = min(hi, a3[k] - 1);
             }
         }
         // flatten the 32 spans into fragments
@@ -151,14 +166,22 @@ __device__ __forceinline__ void raster_rows(const FwdParams& p, WarpScratch& ws,
         }
         const int nfrag = __shfl_sync(0xffffffffu, sincl, 31);
         ws.spanpre[lane] = sincl - n;
+        const bool frag_table = nfrag <= kOwnTable;
+        if (frag_table)
+            for (int j = 0; j < n; j++) ws.fragown[sincl - n + j] = (uint8_t)lane;
         __syncwarp();
         for (int fb = 0; fb < nfrag; fb += 32) {
             const int i = fb + lane;
-            int a = 0, bnd = 32;
+            int a = 0;
+            if (frag_table) {
+                if (i < nfrag) a = ws.fragown[i];
+            } else {
+                int bnd = 32;
 #pragma unroll
-            for (int it = 0; it < 5; it++) {
-                const int mid = (a + bnd) >> 1;
-                if (ws.spanpre[mid] <= i) a = mid; else bnd = mid;
+                for (int it = 0; it < 5; it++) {
+                    const int mid = (a + bnd) >> 1;
+                    if (ws.spanpre[mid] <= i) a = mid; else bnd = mid;
+                }
             }
             // all lanes take part in the shuffles; lanes past the end evaluate nothing
             const int o_own = __shfl_sync(0xffffffffu, own, a);
@@ -178,7 +201,7 @@ __device__ __forceinline__ void raster_rows(const FwdParams& p, WarpScratch& ws,
                 }
             }
         }
-        __syncwarp();  // spanpre is rewritten by the next pass
+        __syncwarp();  // spanpre / fragown are rewritten by the next pass
     }
 }
 
@@ -248,8 +271,11 @@ __global__ void __launch_bounds__(kFaceWarps * 32) k_raster_faces(const __grid_c
         const int nrows = __shfl_sync(0xffffffffu, incl, 31);
         if (nrows == 0) continue;
         ws.rowpre[lane] = incl - h;
+        const bool row_table = nrows <= kOwnTable;
+        if (row_table)
+            for (int j = 0; j < h; j++) ws.rowown[incl - h + j] = (uint8_t)lane;
         __syncwarp();
-        raster_rows(p, ws, pc, b, nrows, g << 5, lane);
+        raster_rows(p, ws, pc, b, nrows, g << 5, lane, row_table);
         __syncwarp();  // the scratch is rewritten by the next unit
     }
 }
@@ -297,7 +323,7 @@ __global__ void __launch_bounds__(256) k_raster_big(const __grid_constant__ FwdP
             const int h = yhi - ylo + 1;
             ws.rowpre[lane] = lane == 0 ? 0 : h;  // lane 0 owns rows [0, h); the other prefix entries lie past the end
             __syncwarp();
-            raster_rows(p, ws, pc, b, h, f, lane);  // face_base + slot 0 = f
+            raster_rows(p, ws, pc, b, h, f, lane, false);  // face_base + slot 0 = f
             __syncwarp();
         }
     }
