@@ -351,12 +351,14 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
+    for (;;) {
+        uint32_t done;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                      : "=r"(done)
                      : "r"(smem_u32(bar)), "r"(parity)
                      : "memory");
+        if (done) break;
+        __nanosleep(64);  // do not burn issue slots of the warps that are still computing
     }
 }
 
