@@ -56,6 +56,15 @@ NUM_SMS = 148
 
 from neural_renderer_b200.distributed import shard_range  # noqa: E402,F401  (re-exported for the tests)
 
+_JSON_OUT = None
+
+
+def emit(obj):
+    """the one JSON line of the run, on the process' original stdout"""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
 
 def algorithmic_bytes(B, F, S, ts):
     """compulsory traffic of the RGB passes (inputs once, outputs + saved maps once)."""
@@ -82,8 +91,11 @@ def kernel_bytes(B, F, S, ts):
     return {
         # faces in, boxes out (per launch; it runs once per pass)
         "k_face_bbox": 36 * B * F + 8 * B * F + B * ((F + 31) // 32) * 8,
-        # the whole forward pass' compulsory traffic (the faces are the 36*B*F k_face_bbox also reads: counted once, here)
-        "k_raster_tile": 36 * B * F + 12 * T * B * F + 32 * P,
+        # forward: z-buffer fill; faces in + one 8-byte z-buffer reduction per pixel (records: L2); z-buffer in + textures
+        # in + every output map out (the pass-level figure is SURVEY.md's 36*B*F + 12*T*B*F + 32*P, see roofline_fwd)
+        "memset_zbuf": 8 * P,
+        "k_raster_faces": 36 * B * F + 8 * P,
+        "k_resolve": 8 * P + 12 * T * B * F + 32 * P,
         # zero-fill of grad_faces + grad_textures
         "memset_grads": 36 * B * F + 12 * T * B * F,
         # K6: grad_rgb 12 + fim 4 + weight_map 12 + depth_map 4 per pixel in, grad_textures out (reductions)
@@ -548,7 +560,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     distributed = world > 1
-    # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG) goes to stderr
+    # stdout carries exactly ONE JSON line: whatever libraries write to file descriptor 1 meanwhile (NCCL prints its
+    # version banner there) is diverted to stderr; the line itself goes to the saved descriptor at the very end
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     w = WORKLOAD
     B, F, S, ts = w["batch_per_gpu"], w["num_faces"], w["image_size"], w["texture_size"]
@@ -574,9 +591,9 @@ def main():
     if args.workload == "shared_mesh":  # stand-alone form of the shared-mesh measurement
         sm = shared_mesh_measure(args, world, rank, dev, barrier, distributed)
         if rank == 0:
-            print(json.dumps(dict({"metric": "Mpixels/s fwd+bwd, shared mesh, viewpoint-sharded", "higher_is_better": True,
-                                   "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                                   "impl": "ours", "warmup": 3, "config": {"workload": sm["workload"]}}, **sm)))
+            emit(dict({"metric": "Mpixels/s fwd+bwd, shared mesh, viewpoint-sharded", "higher_is_better": True,
+                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                       "impl": "ours", "warmup": 3, "config": {"workload": sm["workload"]}}, **sm))
         if distributed:
             dist.destroy_process_group()
         return
@@ -706,7 +723,8 @@ def main():
         kern = {k: round(v / nprof, 5) for k, v in per.items()}
         launches = {k: count[k] // nprof for k in count}
         out["kernels_ms_per_step"] = kern
-        fwd_ms = kern.get("k_raster_tile", 0.0) + kern.get("k_face_bbox", 0.0) / max(launches.get("k_face_bbox", 1), 1)
+        fwd_names = ("memset_zbuf", "k_raster_faces", "k_raster_big", "k_resolve")
+        fwd_ms = sum(kern.get(k, 0.0) for k in fwd_names)
         bwd_ms = sum(v for k, v in kern.items()) - fwd_ms
 
         counts = {}
@@ -738,7 +756,7 @@ def main():
         if dom and dom in rk:
             out["roofline"] = dict(rk[dom], kernel=dom,
                                    note="the dominant kernel's OWN algorithmic bytes / its duration (CUDA events)")
-        out["roofline_fwd"] = dict(roof(fwd_bytes, fwd_ms), kernels="k_face_bbox + k_raster_tile",
+        out["roofline_fwd"] = dict(roof(fwd_bytes, fwd_ms), kernels=" + ".join(fwd_names),
                                    note="forward rasterize pass, 391.5 MB algorithmic (SURVEY.md 8(d))")
         out["roofline_bwd"] = dict(roof(bwd_bytes, bwd_ms),
                                    kernels="memset_grads + k_texture_grad + k_face_bbox + k_strip_bin x2 + k_strip_scan + k_edge_scan",
@@ -747,7 +765,7 @@ def main():
         # issue-slot roofline of the kernels the HBM roof does not describe (warp instructions from the ncu capture)
         sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
         issue = {}
-        for k in ("k_edge_scan", "k_raster_tile"):
+        for k in ("k_edge_scan", "k_resolve", "k_raster_faces"):
             c = counts.get("kernels", {}).get(k)
             if c and c.get("warp_instructions") and kern.get(k):
                 peak_ips = NUM_SMS * 4 * sm_hz
@@ -816,7 +834,7 @@ def main():
 
     sampler.stop()
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if distributed:
         dist.destroy_process_group()
 
@@ -910,7 +928,7 @@ def reference_arm(args, world, rank, local_rank):
             "e2e": {"value": round(value, 4), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         })
-    print(json.dumps(base))
+    emit(base)
 
 
 if __name__ == "__main__":

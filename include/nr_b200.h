@@ -77,6 +77,12 @@ extern "C" {
                                      /* neither bit = both parts; a caller that wants to start a collective on the texture   */
                                      /* gradient while the edge scan runs calls TEXTURES first, then FACES                   */
 
+#define NR_FWD_STAGE_TEXTURES 0x10000u /* forward, RGB without anti-aliasing: stage the texture cubes of every pixel row in     */
+                                       /* shared memory with bulk asynchronous copies (cp.async.bulk / TMA, one mbarrier per CTA)  */
+                                       /* before sampling.  Same pixels; measured SLOWER than the direct gather on B200            */
+                                       /* (DESIGN.md section 4), hence opt-in.  Ignored when the cube size is not a multiple of   */
+                                       /* 16 bytes or `textures` is not 16-byte aligned.                                           */
+
 typedef struct nr_b200_forward_args {
     uint32_t struct_size; /* sizeof(nr_b200_forward_args), for ABI evolution */
     uint32_t flags;

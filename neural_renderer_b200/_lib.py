@@ -27,6 +27,7 @@ NR_INDICES_SHARED = 0x1000
 NR_TEX_SHARED = 0x2000
 NR_BWD_PART_TEXTURES = 0x4000
 NR_BWD_PART_FACES = 0x8000
+NR_FWD_STAGE_TEXTURES = 0x10000
 
 ABI_VERSION = 3
 

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
     static_assert(kFaceQueue <= 512 && kTaskCap <= 4096, "task word layout");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = p.S, W = p.W;
-    const int Sp = (S + 15) & ~15, npair = Sp >> 1;  // lines padded to whole 16-pixel windows (zero-staged)
+    const int Sp = (S + 1) & ~1, npair = Sp >> 1;
     float4* P = reinterpret_cast<float4*>(smem_raw);
     float4* Q = P + (size_t)W * npair;
     float4* ci = Q + (size_t)W * npair;
@@ -462,22 +462,12 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                             p10 = nr::to_pixel(__ldg(nr::face_vertex(p.src, b, f, (e + 1) % 3) + axis), fS);
                 const int lo = max(__float2int_rz(fmaxf(ceilf(fminf(p00, p10)), 0.0f)), l0);
                 const int hi = min(__float2int_rz(fminf(fmaxf(p00, p10), (float)(S - 1))), lhi);
-                if (lo > hi) continue;
-                // Only what decides whether the slot is a task and how long its out-scan is: the crossing
-                // (rasterize.py:567-573) with the slope hoisted out of the line loop.  The full geometry of a task is
-                // set up once, by the lane that runs it (phase 3).
-                const float p01 = nr::to_pixel(__ldg(nr::face_vertex(p.src, b, f, e) + (1 - axis)), fS),
-                            p11 = nr::to_pixel(__ldg(nr::face_vertex(p.src, b, f, (e + 1) % 3) + (1 - axis)), fS);
-                const bool lt = p00 < p10;
-                const int dir = (axis == 0) ? (lt ? -1 : 1) : (lt ? 1 : -1);
-                const float slope = __fdiv_rn(__fsub_rn(p11, p01), __fsub_rn(p10, p00));
                 for (int d0 = lo; d0 <= hi; d0++) {
                     const int line = d0 - l0;
-                    const float d1_cross = __fmaf_rn(__fsub_rn((float)d0, p00), slope, p01);
-                    const int d1_in = __float2int_rz(dir > 0 ? floorf(d1_cross) : ceilf(d1_cross));
-                    const int d1_out = d1_in + dir;
-                    if (d1_in < 0 || d1_in >= S || d1_out < 0 || d1_out >= S) continue;
-                    const int L = dir > 0 ? S - 1 - d1_in : d1_in;  // out-scan length (the in-scan is a few pixels)
+                    Task T;
+                    task_setup(f, e, line, T);
+                    if (!T.valid) continue;
+                    const int L = max(T.out_to - T.out_from + 1, 0) + 2 * max(T.in_to - T.in_from + 1, 0);
                     const int bucket = min(L >> len_shift, 31);
                     const int rank = atomicAdd(&s_hist[bucket], 1);
                     const int t = atomicAdd(&s_ntask, 1);
@@ -566,41 +556,26 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                     const int o_dir = __shfl_sync(0xffffffffu, T.dir, src);
                     if (!__any_sync(0xffffffffu, o_from <= o_to)) continue;
                     f32x2 a0 = pk(0.f, 0.f), a1 = pk(0.f, 0.f);  // positive sums; the sign is applied at the hand-over
-                    // An out-scan covers [o_from, o_to], from the pixel outside the crossing to an image border.  It is
-                    // walked in whole 16-pixel WINDOWS (8 pairs = 128 bytes of P and of Q), half a window (4 pairs, one per
-                    // lane) per step.  The two tasks that share a quarter-warp -- the unit a 16-byte shared-memory load
-                    // is served in -- always read OPPOSITE halves of their windows: even slots ascend from the first window
-                    // starting with its low half, odd slots descend from the last window starting with its high half.  Bytes
-                    // 0..63 and 64..127 of a 128-byte aligned window live in disjoint banks, so the loads are conflict-free
-                    // whatever lines and positions the two tasks have (random 64-byte spans collide 7 times out of 8).
-                    // Pixels of the first / last window that lie outside the scan are masked arithmetically: a pixel belongs
-                    // to the out-scan iff (d1 - d1_cross) * dir > 0 (the crossing pixel inside the face has <= 0), and
-                    // max(min(dg, (d1 - d1_cross) * dir * 1e30), 0) is relu(dg) there and 0 elsewhere; the padding pixels
-                    // beyond the raster are staged as zeros.
-                    if (o_from <= o_to) {
+                    // An out-scan runs from the crossing to an image border, so only the pixel pair at the crossing end
+                    // can hold a pixel outside [o_from, o_to] (the padding pixel of an odd raster size is staged as
+                    // zeros).  Pairs are therefore walked FROM the crossing: the first step is peeled with the range
+                    // gates, the steady-state loop carries none.
+                    const int pa = o_from >> 1, npairs = (o_to >> 1) - pa + 1;
+                    if (o_from <= o_to && j < npairs) {
                         const bool up = o_dir > 0;
-                        const int wa = o_from >> 4, wb = o_to >> 4;
-                        const int nsteps = 2 * (wb - wa + 1);
-                        const bool odd = (qd & 1) != 0;
                         const f32x2 nc0 = pk(-o_c0, -o_c0), nc1 = pk(-o_c1, -o_c1), nc2 = pk(-o_c2, -o_c2), nca = pk(-o_ca, -o_ca);
-                        const int pp = odd ? (wb << 3) + 4 + j : (wa << 3) + j;
+                        int pp = up ? pa + j : (o_to >> 1) - j;
                         const float4* Pp = P + (size_t)o_line * npair + pp;
                         const float4* Qp = Q + (size_t)o_line * npair + pp;
                         const float2* Rp = R + (size_t)o_line * npair + pp;
-                        const int dpp = odd ? -4 : 4;
-                        // pixel positions advance exactly (small integers in fp32); d1 - d1_cross, dist_v = (d1 - d1_cross) *
-                        // k_v +- eps and the membership term are re-evaluated from the position in every step, so nothing
-                        // drifts towards the crossing, where 1 / dist is largest (odd slots walk TOWARDS it)
-                        const float fp = (float)(pp << 1);
-                        f32x2 fp2 = pk(fp, fp + 1.0f);
-                        const f32x2 ndc2 = pk(-o_dc, -o_dc), k0_2 = pk(o_k0, o_k0), k1_2 = pk(o_k1, o_k1), e0_2 = pk(o_e0, o_e0),
-                                    e1_2 = pk(o_e1, o_e1);
-                        const float big = up ? 1e30f : -1e30f;
-                        const f32x2 big2 = pk(big, big);
-                        const float s8 = odd ? -8.0f : 8.0f;
-                        const f32x2 s8_2 = pk(s8, s8);
-#pragma unroll 2
-                        for (int i = 0; i < nsteps; i++) {
+                        const int dpp = up ? 4 : -4;
+                        const float ta = __fsub_rn((float)(pp << 1), o_dc);  // d1 - d1_cross of the lane's first pixel
+                        const f32x2 tt2 = pk(ta, ta + 1.0f);
+                        // dist_v = (d1 - d1_cross) * k_v +- eps, advanced by +-8 pixels per step
+                        f32x2 d0_2 = fma2(tt2, pk(o_k0, o_k0), pk(o_e0, o_e0)), d1_2 = fma2(tt2, pk(o_k1, o_k1), pk(o_e1, o_e1));
+                        const float s8 = up ? 8.0f : -8.0f;
+                        const f32x2 dk0 = pk(s8 * o_k0, s8 * o_k0), dk1 = pk(s8 * o_k1, s8 * o_k1);
+                        auto diff_grad = [&](float& dga, float& dgb) {
                             const float4 pv = *Pp;
                             f32x2 dg2 = fma2(nc0, pk(pv.z, pv.w), pk(pv.x, pv.y));
                             if (kMode != 2) {
@@ -612,21 +587,32 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                                 const float2 rv = *Rp;
                                 dg2 = fma2(nca, pk(rv.x, rv.y), dg2);
                             }
-                            const f32x2 tt2 = add2(fp2, ndc2);
-                            const f32x2 d0_2 = fma2(tt2, k0_2, e0_2), d1_2 = fma2(tt2, k1_2, e1_2), m2 = mul2(tt2, big2);
-                            float dga, dgb, ma, mb, qa, qb;
                             upk(dg2, dga, dgb);
-                            upk(m2, ma, mb);
-                            // relu gate of rasterize.py:647 (max drops a NaN diff_grad) + membership
-                            dga = fmaxf(fminf(dga, ma), 0.0f);
-                            dgb = fmaxf(fminf(dgb, mb), 0.0f);
+                        };
+                        auto accumulate = [&](float dga, float dgb) {
+                            float qa, qb;
                             upk(mul2(d0_2, d1_2), qa, qb);
                             // one reciprocal serves both vertices: dg / d0 = dg * d1 / (d0 * d1)
                             const f32x2 t2 = mul2(pk(dga, dgb), pk(rcp_approx(qa), rcp_approx(qb)));
                             a0 = fma2(t2, d1_2, a0);
                             a1 = fma2(t2, d0_2, a1);
-                            fp2 = add2(fp2, s8_2);
+                            d0_2 = add2(d0_2, dk0);
+                            d1_2 = add2(d1_2, dk1);
                             Pp += dpp; Qp += dpp; Rp += dpp;
+                        };
+                        {   // first step: relu gate of rasterize.py:647 (max drops a NaN diff_grad) + range ends
+                            float dga, dgb;
+                            diff_grad(dga, dgb);
+                            const int y0 = pp << 1;
+                            dga = (y0 >= o_from) ? fmaxf(dga, 0.0f) : 0.0f;
+                            dgb = (y0 + 1 <= o_to) ? fmaxf(dgb, 0.0f) : 0.0f;
+                            accumulate(dga, dgb);
+                        }
+#pragma unroll 2
+                        for (int i = j + 4; i < npairs; i += 4) {
+                            float dga, dgb;
+                            diff_grad(dga, dgb);
+                            accumulate(fmaxf(dga, 0.0f), fmaxf(dgb, 0.0f));
                         }
                     }
                     float s0a, s0b, s1a, s1b;
@@ -848,11 +834,11 @@ BinLayout bin_layout(int B, int F, int S, int rec_bytes) {
     if (const char* env = getenv("NR_B200_STRIP_KB")) { strip_bytes = (size_t)atoi(env) * 1024; strip_forced = true; }
 #endif
     int W = kMaxLines;
-    while (W > 1 && (size_t)W * ((S + 15) & ~15) * rec_bytes > strip_bytes) W >>= 1;
+    while (W > 1 && (size_t)W * ((S + 1) & ~1) * rec_bytes > strip_bytes) W >>= 1;
     // one-line strips pay the per-CTA front end (staging, face list, task sort) per line: two lines are worth twice
     // the shared memory up to 32 KB (raster 512: 3.5 -> 3.3 ms at the Renderer-default shape, 4.3 -> 3.2 ms at 70 k
     // faces); beyond that the lost occupancy costs more (measured with 64 KB)
-    if (W == 1 && !strip_forced && (size_t)2 * ((S + 15) & ~15) * rec_bytes <= 2 * (size_t)kStripBytesDefault) W = 2;
+    if (W == 1 && !strip_forced && (size_t)2 * ((S + 1) & ~1) * rec_bytes <= 2 * (size_t)kStripBytesDefault) W = 2;
     L.W = W;
     L.w_log2 = 0;
     while ((1 << L.w_log2) < W) L.w_log2++;
@@ -962,7 +948,7 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
         p.debug_skip = getenv("NR_B200_ES_SKIP") ? atoi(getenv("NR_B200_ES_SKIP")) : 0;
 #endif
         while ((2 * S) >> p.len_shift > 32) p.len_shift++;
-        const size_t smem = (size_t)W * ((S + 15) & ~15) * rec_bytes;
+        const size_t smem = (size_t)W * ((S + 1) & ~1) * rec_bytes;
         if (smem > 160 * 1024) return NR_ERR_UNSUPPORTED;
         const int nstrips = L.nstrips;
         char* wsb = (char*)a->workspace;

@@ -33,6 +33,14 @@ USE_UNSAFE_IMPLEMENTATION = False
 # rasterize.py:389 fetches the vertex depths for texture sampling from batch item 0.  Reference-exact by default;
 # NEURAL_RENDERER_B200_FIX_TEXTURE_DEPTH=1 (or set_reference_exact(False)) samples with each item's own depths.
 _REFERENCE_EXACT = not int(os.environ.get("NEURAL_RENDERER_B200_FIX_TEXTURE_DEPTH", "0"))
+# NR_FWD_STAGE_TEXTURES (texture cubes staged in shared memory with cp.async.bulk): same pixels, measured slower than the
+# direct gather on B200 -- kept selectable for measurements and tests, off by default.
+_STAGE_TEXTURES = False
+
+
+def set_stage_textures(flag):
+    global _STAGE_TEXTURES
+    _STAGE_TEXTURES = bool(flag)
 
 
 def set_reference_exact(flag):
@@ -319,6 +327,8 @@ def _run(faces, textures, image_size, anti_aliasing, near, far, eps, background_
                        return_depth, geom.device, batch_size)
     if return_rgb and textures_fill_back:
         cfg.flags |= _lib.NR_TEX_FILL_BACK
+    if return_rgb and _STAGE_TEXTURES:
+        cfg.flags |= _lib.NR_FWD_STAGE_TEXTURES
     return _RasterizeFunction.apply(geom, textures if return_rgb else None, face_light if return_rgb else None, cfg,
                                     indices)
 
