@@ -251,7 +251,7 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f
 //   ci[i] = {I0, I1, I2, fim}        colours and face index per pixel: task set-up and the short in-scan only
 // kMode: 1 = rgb, 2 = alpha only (g0 = g_alpha, I0 = alpha), 3 = rgb + alpha
 //@phase prologue
-template <int kMode, int kThreads>
+template <int kMode, int kThreads, bool kIdx>
 __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const __grid_constant__ BwdParams p) {
     constexpr int kFaceQueue = 2 * kThreads, kTaskCap = 8 * kThreads;
     static_assert(kFaceQueue <= 512 && kTaskCap <= 4096, "task word layout");
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
     };
     auto task_setup = [&](int f, int e, int line, Task& T) {
         const int pi0 = e, pi1 = (e + 1) % 3, pi2 = (e + 2) % 3;
-        const float *v0 = nr::face_vertex(p.src, b, f, pi0), *v1 = nr::face_vertex(p.src, b, f, pi1);
+        const float *v0 = nr::face_vertex_t<kIdx>(p.src, b, f, pi0), *v1 = nr::face_vertex_t<kIdx>(p.src, b, f, pi1);
         const int a = axis, c = 1 - axis;
         T.pi0 = pi0; T.pi1 = pi1;
         T.valid = false;
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
             T.out_to = min(max(T.d1_out, lim), S - 1);
         }
         // in-scan: from the inside pixel to where this line leaves the face through one of the other two edges
-        const float* v2 = nr::face_vertex(p.src, b, f, pi2);
+        const float* v2 = nr::face_vertex_t<kIdx>(p.src, b, f, pi2);
         const float p20 = nr::to_pixel(__ldg(v2 + a), fS), p21 = nr::to_pixel(__ldg(v2 + c), fS);
         float ba, bb, ea, eb;
         if (__fmul_rn(__fsub_rn(fd0, p00), __fsub_rn(fd0, p20)) < 0.0f) { ba = p00; bb = p01; ea = p20; eb = p21; }
@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                 const int e = i % 3, q = q0 + i / 3;
                 const int f = s_faceq[q];
                 // lines of the strip that this edge spans (same truncating conversions as task_setup)
-                const float p00 = nr::to_pixel(__ldg(nr::face_vertex(p.src, b, f, e) + axis), fS),
-                            p10 = nr::to_pixel(__ldg(nr::face_vertex(p.src, b, f, (e + 1) % 3) + axis), fS);
+                const float p00 = nr::to_pixel(__ldg(nr::face_vertex_t<kIdx>(p.src, b, f, e) + axis), fS),
+                            p10 = nr::to_pixel(__ldg(nr::face_vertex_t<kIdx>(p.src, b, f, (e + 1) % 3) + axis), fS);
                 const int lo = max(__float2int_rz(fmaxf(ceilf(fminf(p00, p10)), 0.0f)), l0);
                 const int hi = min(__float2int_rz(fminf(fmaxf(p00, p10), (float)(S - 1))), lhi);
                 for (int d0 = lo; d0 <= hi; d0++) {
@@ -628,8 +628,8 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
                     const float r0 = __shfl_sync(0xffffffffu, s0, (lane & 7) << 2), r1 = __shfl_sync(0xffffffffu, s1, (lane & 7) << 2);
                     if ((lane >> 3) == sub) { acc0 -= r0; acc1 -= r1; }
                 }
-                if (acc0 != 0.0f) { float* g = nr::face_grad_vertex(p.dst, b, fn, T.pi0); if (g) atomicAdd(g + (1 - axis), acc0); }
-                if (acc1 != 0.0f) { float* g = nr::face_grad_vertex(p.dst, b, fn, T.pi1); if (g) atomicAdd(g + (1 - axis), acc1); }
+                if (acc0 != 0.0f) { float* g = nr::face_grad_vertex_t<kIdx>(p.dst, b, fn, T.pi0); if (g) atomicAdd(g + (1 - axis), acc0); }
+                if (acc1 != 0.0f) { float* g = nr::face_grad_vertex_t<kIdx>(p.dst, b, fn, T.pi1); if (g) atomicAdd(g + (1 - axis), acc1); }
             }
             __syncthreads();
             if (tid < 32) s_hist[tid] = 0;
@@ -663,9 +663,16 @@ __global__ void __launch_bounds__(256) k_texture_grad(const __grid_constant__ Bw
         const float zp = __ldg(p.dmap + (size_t)b * plane + i);
         const int zb = (p.flags & NR_TEX_Z_BATCH0) ? 0 : b;
         const int ts = p.ts;
-        const nr::TexCoord tc = nr::texture_coords(w, zp, __ldg(nr::face_vertex(p.src, zb, fn, 0) + 2),
-                                                   __ldg(nr::face_vertex(p.src, zb, fn, 1) + 2),
-                                                   __ldg(nr::face_vertex(p.src, zb, fn, 2) + 2), ts, p.tex_cmp, p.tex_val);
+        float z0, z1, z2;
+        if (p.src.idx == nullptr) {
+            const float* v = p.src.faces + ((size_t)zb * p.F + fn) * 9;
+            z0 = __ldg(v + 2); z1 = __ldg(v + 5); z2 = __ldg(v + 8);
+        } else {
+            z0 = __ldg(nr::face_vertex_t<true>(p.src, zb, fn, 0) + 2);
+            z1 = __ldg(nr::face_vertex_t<true>(p.src, zb, fn, 1) + 2);
+            z2 = __ldg(nr::face_vertex_t<true>(p.src, zb, fn, 2) + 2);
+        }
+        const nr::TexCoord tc = nr::texture_coords(w, zp, z0, z1, z2, ts, p.tex_cmp, p.tex_val);
         // NR_TEX_FILL_BACK: the reversed copy of face f - F/2 shares that face's cube, axes reversed
         int cube = fn, ncubes = p.F;
         bool rev = false;
@@ -799,13 +806,18 @@ inline float float_le(double d) {
     return f;
 }
 
+template <int kMode, int kT, bool kIdx>
+int launch_edge_scan_i(const BwdParams& p, int nstrips, size_t smem, cudaStream_t stream) {
+    static nr_internal::SmemOptIn optin;
+    if (optin.ensure(k_edge_scan<kMode, kT, kIdx>, smem) != cudaSuccess) return NR_ERR_CUDA;
+    nr_internal::LaunchScope ls("k_edge_scan", stream);
+    k_edge_scan<kMode, kT, kIdx><<<dim3(nstrips, 2, p.B), kT, smem, stream>>>(p);
+    return NR_OK;
+}
 template <int kMode, int kT>
 int launch_edge_scan_t(const BwdParams& p, int nstrips, size_t smem, cudaStream_t stream) {
-    static nr_internal::SmemOptIn optin;
-    if (optin.ensure(k_edge_scan<kMode, kT>, smem) != cudaSuccess) return NR_ERR_CUDA;
-    nr_internal::LaunchScope ls("k_edge_scan", stream);
-    k_edge_scan<kMode, kT><<<dim3(nstrips, 2, p.B), kT, smem, stream>>>(p);
-    return NR_OK;
+    return p.src.idx ? launch_edge_scan_i<kMode, kT, true>(p, nstrips, smem, stream)
+                     : launch_edge_scan_i<kMode, kT, false>(p, nstrips, smem, stream);
 }
 
 template <int kMode>
@@ -814,7 +826,10 @@ int launch_edge_scan(const BwdParams& p, int nstrips, size_t smem, cudaStream_t 
 #ifdef NR_B200_TUNING
     if (const char* env = getenv("NR_B200_ES_THREADS")) threads = atoi(env);
 #endif
+#ifdef NR_B200_TUNING
     if (threads == 256) return launch_edge_scan_t<kMode, 256>(p, nstrips, smem, stream);
+#endif
+    (void)threads;
     return launch_edge_scan_t<kMode, 128>(p, nstrips, smem, stream);
 }
 

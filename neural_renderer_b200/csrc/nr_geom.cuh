@@ -21,12 +21,17 @@ struct FaceSrc {
     int F, Nv;
 };
 
-// pointer to the 3 floats (x, y, z) of vertex k of face f of batch item b
-__device__ __forceinline__ const float* face_vertex(const FaceSrc& s, int b, int f, int k) {
-    if (s.idx == nullptr) return s.faces + (((size_t)b * s.F + f) * 3 + k) * 3;
+// pointer to the 3 floats (x, y, z) of vertex k of face f of batch item b; the hot kernels are compiled once per
+// geometry form (kIndexed) so that the materialised-faces path carries no trace of the indexed one
+template <bool kIndexed>
+__device__ __forceinline__ const float* face_vertex_t(const FaceSrc& s, int b, int f, int k) {
+    if (!kIndexed) return s.faces + (((size_t)b * s.F + f) * 3 + k) * 3;
     const int i = __ldg(s.idx + (size_t)b * s.idx_bstride + (size_t)f * 3 + k);
     if ((unsigned)i >= (unsigned)s.Nv) return kZeroVertex;
     return s.vertices + ((size_t)b * s.Nv + i) * 3;
+}
+__device__ __forceinline__ const float* face_vertex(const FaceSrc& s, int b, int f, int k) {
+    return s.idx == nullptr ? face_vertex_t<false>(s, b, f, k) : face_vertex_t<true>(s, b, f, k);
 }
 
 __device__ __forceinline__ void load_face(const FaceSrc& s, int b, int f, float c[9]) {
@@ -57,11 +62,15 @@ struct FaceGrad {
 
 // where d loss / d (x, y, z) of vertex k of face f accumulates; nullptr for an out-of-range index (skipped, like
 // nr_b200_vertices_to_faces_backward)
-__device__ __forceinline__ float* face_grad_vertex(const FaceGrad& g, int b, int f, int k) {
-    if (g.idx == nullptr) return g.grad_faces + (((size_t)b * g.F + f) * 3 + k) * 3;
+template <bool kIndexed>
+__device__ __forceinline__ float* face_grad_vertex_t(const FaceGrad& g, int b, int f, int k) {
+    if (!kIndexed) return g.grad_faces + (((size_t)b * g.F + f) * 3 + k) * 3;
     const int i = __ldg(g.idx + (size_t)b * g.idx_bstride + (size_t)f * 3 + k);
     if ((unsigned)i >= (unsigned)g.Nv) return nullptr;
     return g.grad_vertices + ((size_t)b * g.Nv + i) * 3;
+}
+__device__ __forceinline__ float* face_grad_vertex(const FaceGrad& g, int b, int f, int k) {
+    return g.idx == nullptr ? face_grad_vertex_t<false>(g, b, f, k) : face_grad_vertex_t<true>(g, b, f, k);
 }
 
 }  // namespace nr
