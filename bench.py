@@ -366,6 +366,8 @@ def shared_mesh_measure(args, world, rank, dev, barrier, distributed):
     renderer = nr.Renderer()
     renderer.image_size, renderer.anti_aliasing, renderer.fill_back = S, False, False
     renderer.eye = eyes
+    renderer.reference_exact = False  # viewpoint shards: every view samples with its own depths (rasterize.py:389 would
+    #                                   tie the result to which viewpoint happens to be item 0 of a rank's shard)
     grad = torch.randn((V, 3, S, S), generator=torch.Generator().manual_seed(99 + rank)).to(dev)
     steps, warmup = max(3, min(args.steps, 5)), 3
 

@@ -36,6 +36,13 @@
 #include "nr_internal.h"
 #include "nr_math.cuh"
 
+#ifndef NR_ES_CTAS_PER_1024
+#define NR_ES_CTAS_PER_1024 8   // k_edge_scan CTAs per SM at 128 threads (8 = 64 registers)
+#endif
+#ifndef NR_TG_MIN_CTAS
+#define NR_TG_MIN_CTAS 6
+#endif
+
 namespace {
 
 // Phase-ablation switches exist only in experiment builds (-DNR_B200_DEBUG_KNOBS); the product never drops a term.
@@ -252,7 +259,7 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f
 // kMode: 1 = rgb, 2 = alpha only (g0 = g_alpha, I0 = alpha), 3 = rgb + alpha
 //@phase prologue
 template <int kMode, int kThreads, bool kIdx>
-__global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThreads / 8) k_edge_scan(const __grid_constant__ BwdParams p) {
     constexpr int kFaceQueue = 2 * kThreads, kTaskCap = 8 * kThreads;
     static_assert(kFaceQueue <= 512 && kTaskCap <= 4096, "task word layout");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -643,7 +650,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_edge_scan(const _
 }
 
 // --------------------------------------------------------------------------------------------- k_texture_grad
-__global__ void __launch_bounds__(256) k_texture_grad(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(256, NR_TG_MIN_CTAS) k_texture_grad(const __grid_constant__ BwdParams p) {
     const int S = p.S;
     const size_t plane = (size_t)S * S;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel within the image (image orientation)

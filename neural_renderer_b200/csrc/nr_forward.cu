@@ -50,6 +50,13 @@ constexpr int kBigArea = 1024;         // faces whose (clipped) pixel box is lar
 constexpr int kBigTile = 64;           // screen tile of k_raster_big
 constexpr int kRecWords = 12;          // {inv[9], z0, z1, z2}
 constexpr int kOwnTable = 256;         // rows / fragments per pass whose owner lane is looked up instead of searched
+#ifndef NR_FACES_MIN_CTAS
+#define NR_FACES_MIN_CTAS 5
+#endif
+#ifndef NR_RESOLVE_MIN_CTAS
+#define NR_RESOLVE_MIN_CTAS 8  // CTAs of 256 threads per SM the resolve pass is compiled for (32 registers: the pass is
+                               // latency-bound on its dependent gathers, occupancy beats per-thread ILP -- measured)
+#endif
 constexpr uint32_t kStageBytes = 32 * 1024;  // shared memory of a k_resolve CTA for staged texture cubes
 
 struct FwdParams {
@@ -212,7 +219,7 @@ __device__ __forceinline__ void fill_centres(float* table, int S, int tid, int n
 
 // ------------------------------------------------------------------------------------------ k_raster_faces
 //@phase k_raster_faces: cull + K1 + records
-__global__ void __launch_bounds__(kFaceWarps * 32) k_raster_faces(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(kFaceWarps * 32, NR_FACES_MIN_CTAS) k_raster_faces(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw);
     float* centres = reinterpret_cast<float*>(smem_raw + sizeof(WarpScratch) * kFaceWarps);
@@ -463,8 +470,9 @@ __device__ __forceinline__ Shaded shade_pixel(const FwdParams& p, int b, unsigne
 // 83 us for the direct gather (ts = 4; 74 vs 62 us at ts = 2) -- a whole 768-byte cube is copied for the 8 texels a pixel
 // blends, and the L1 data stage (the unit both variants saturate first) pays for the shared-memory writes of the copy
 // plus the bank conflicts of the 24 scattered reads.  The direct gather is therefore the default.
-template <bool kAA, bool kStage, bool kLit>
-__global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ FwdParams p, int nslots) {
+template <bool kAA, int kTex, bool kLit>
+__global__ void __launch_bounds__(256, kAA ? 5 : NR_RESOLVE_MIN_CTAS) k_resolve(const __grid_constant__ FwdParams p, int nslots) {
+    constexpr bool kStage = kTex == 1;  // kTex: 0 = every texel straight from global memory, 1 = cubes staged with cp.async.bulk
     extern __shared__ __align__(16) unsigned char stage_raw[];
     __shared__ uint64_t s_bar;
     __shared__ int s_runs[8];
@@ -714,15 +722,17 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
             nslots = (int)std::min<uint32_t>(kStageBytes / cube_bytes, (uint32_t)bx);
             smem = (size_t)nslots * cube_bytes;
         }
-#define NR_RESOLVE(AA, ST, LIT)                                                                     \
+#define NR_RESOLVE(AA, TEX, LIT)                                                                    \
     do {                                                                                            \
         static nr_internal::SmemOptIn optin;                                                        \
-        if (optin.ensure(k_resolve<AA, ST, LIT>, smem) != cudaSuccess) return NR_ERR_CUDA;          \
-        k_resolve<AA, ST, LIT><<<grid, bx, smem, stream>>>(p, nslots);                              \
+        if (optin.ensure(k_resolve<AA, TEX, LIT>, smem) != cudaSuccess) return NR_ERR_CUDA;         \
+        k_resolve<AA, TEX, LIT><<<grid, bx, smem, stream>>>(p, nslots);                             \
     } while (0)
-        if (aa) { if (lit) NR_RESOLVE(true, false, true); else NR_RESOLVE(true, false, false); }
-        else if (stage) { if (lit) NR_RESOLVE(false, true, true); else NR_RESOLVE(false, true, false); }
-        else { if (lit) NR_RESOLVE(false, false, true); else NR_RESOLVE(false, false, false); }
+#define NR_RESOLVE_LIT(AA, TEX) do { if (lit) NR_RESOLVE(AA, TEX, true); else NR_RESOLVE(AA, TEX, false); } while (0)
+        if (aa) NR_RESOLVE_LIT(true, 0);
+        else if (stage) NR_RESOLVE_LIT(false, 1);
+        else NR_RESOLVE_LIT(false, 0);
+#undef NR_RESOLVE_LIT
 #undef NR_RESOLVE
     }
     return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;

@@ -1,5 +1,8 @@
-"""Thin array glue around the hot path, re-expressed with plain torch ops (SURVEY.md section 8(f) "next" rows; not
-CUDA of their own yet).  Each function mirrors the reference function of the same name:
+"""The steps either side of the rasterizer, each mirroring the reference function of the same
+name.  On CUDA float32 tensors the camera pipeline, the per-face light factor and vertices_to_faces run as fused
+kernels behind the C ABI (csrc/nr_glue.cu); the plain torch formulation below them serves CPU tensors and is the
+test oracle of those kernels.  `Renderer` goes one step further and hands vertices + indices to the rasterizer itself
+(NR_FACES_INDEXED), so vertices_to_faces does not run at all on its path.
 
   cross                   cross.py:6-59
   get_points_from_angles  get_points_from_angles.py:6-24

@@ -126,7 +126,7 @@ class _Config:
 
 
 def _make_config(image_size, anti_aliasing, near, far, eps, background_color, return_rgb, return_alpha, return_depth,
-                 device, batch_size):
+                 device, batch_size, reference_exact=None):
     if not any((return_rgb, return_alpha, return_depth)):
         raise Exception("nothing to draw")  # rasterize.py:25-27 raises a bare Exception
     cfg = _Config()
@@ -142,7 +142,7 @@ def _make_config(image_size, anti_aliasing, near, far, eps, background_color, re
         flags |= _lib.NR_RETURN_DEPTH
     if cfg.aa:
         flags |= _lib.NR_ANTI_ALIASING
-    cfg.reference_exact = _REFERENCE_EXACT
+    cfg.reference_exact = _REFERENCE_EXACT if reference_exact is None else bool(reference_exact)
     if cfg.reference_exact:
         flags |= _lib.NR_TEX_Z_BATCH0
     cfg.bg = (0.0, 0.0, 0.0)
@@ -306,7 +306,7 @@ class _RasterizeFunction(torch.autograd.Function):
 
 
 def _run(faces, textures, image_size, anti_aliasing, near, far, eps, background_color, return_rgb, return_alpha,
-         return_depth, face_light=None, textures_fill_back=False, vertices=None):
+         return_depth, face_light=None, textures_fill_back=False, vertices=None, reference_exact=None):
     _check_inputs(faces, textures, return_rgb, face_light, textures_fill_back, vertices)
     indices = None
     if vertices is not None:
@@ -324,7 +324,7 @@ def _run(faces, textures, image_size, anti_aliasing, near, far, eps, background_
         if textures.shape[0] == batch_size > 1 and textures.stride(0) == 0:
             textures = textures[:1]  # an expanded shared texture set: sample it in place (NR_TEX_SHARED)
     cfg = _make_config(image_size, anti_aliasing, near, far, eps, background_color, return_rgb, return_alpha,
-                       return_depth, geom.device, batch_size)
+                       return_depth, geom.device, batch_size, reference_exact)
     if return_rgb and textures_fill_back:
         cfg.flags |= _lib.NR_TEX_FILL_BACK
     if return_rgb and _STAGE_TEXTURES:
@@ -349,6 +349,7 @@ def rasterize_rgbad(
         face_light=None,
         textures_fill_back=False,
         vertices=None,
+        reference_exact=None,
 ):
     """Generate RGB, alpha channel, and depth images from faces and textures (for RGB).  rasterize.py:900-977.
 
@@ -363,10 +364,16 @@ def rasterize_rgbad(
                               shared by the batch) and vertices_to_faces (vertices_to_faces.py:16-21) plus its
                               scatter-add backward run inside the rasterizer: no [B,F,3,3] tensor exists and the
                               gradient arrives in `vertices.grad`
+      reference_exact         True / False overrides the module default (`set_reference_exact`) for this call: the
+                              reference's texture sampler reads the vertex depths of batch item 0 for EVERY item
+                              (rasterize.py:389).  True reproduces that bit for bit; False samples every item with its own
+                              depths -- what one wants for batches of different meshes or cameras (the images of items
+                              b > 0 and grad_textures differ, item 0 and all silhouettes / depths do not)
     `textures` with batch size 1 (or an expanded stride-0 batch) while the geometry batch is larger = one texture set
     shared by every item (a mesh seen from B viewpoints, mesh.py:29-34); its gradient is the sum over the items."""
     rgb, alpha, depth, _, _ = _run(faces, textures, image_size, anti_aliasing, near, far, eps, background_color,
-                                   return_rgb, return_alpha, return_depth, face_light, textures_fill_back, vertices)
+                                   return_rgb, return_alpha, return_depth, face_light, textures_fill_back, vertices,
+                                   reference_exact)
     return {
         'rgb': rgb if return_rgb else None,
         'alpha': alpha if return_alpha else None,
@@ -387,11 +394,13 @@ def rasterize(
         face_light=None,
         textures_fill_back=False,
         vertices=None,
+        reference_exact=None,
 ):
     """RGB images [B,3,H,W] from faces and textures.  rasterize.py:980-1008 (keyword-only extras: rasterize_rgbad)."""
     return rasterize_rgbad(
         faces, textures, image_size, anti_aliasing, near, far, eps, background_color, True, False, False,
-        face_light=face_light, textures_fill_back=textures_fill_back, vertices=vertices)['rgb']
+        face_light=face_light, textures_fill_back=textures_fill_back, vertices=vertices,
+        reference_exact=reference_exact)['rgb']
 
 
 def rasterize_silhouettes(

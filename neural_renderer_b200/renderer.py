@@ -36,8 +36,12 @@ class Renderer(object):
         # rasterization
         self.rasterizer_eps = 1e-3
 
-        # not in the reference: fold lighting / fill_back texture handling into the rasterizer (same pixels)
+        # not in the reference: fold lighting / fill_back texture handling / vertices_to_faces into the rasterizer (same pixels)
         self.fused = True
+        # rasterize.py:389: the reference samples the textures of EVERY batch item with the vertex depths of item 0.
+        # None = module default (reference-exact, see neural_renderer_b200.set_reference_exact); False = every item with
+        # its own depths (batches of different meshes / cameras, viewpoint shards of a multi-GPU run)
+        self.reference_exact = None
 
     def _transform(self, vertices):
         # renderer.py:41-50 (look_at / look, then perspective), fused into one kernel on CUDA
@@ -92,7 +96,7 @@ class Renderer(object):
             return rasterize(
                 indices, textures, self.image_size, self.anti_aliasing, self.near, self.far, self.rasterizer_eps,
                 self.background_color, face_light=light, textures_fill_back=self.fill_back,
-                vertices=self._transform(vertices))
+                vertices=self._transform(vertices), reference_exact=self.reference_exact)
         if self.fill_back:
             faces = torch.cat((faces, faces.flip(2)), dim=1)
             textures = torch.cat((textures, textures.permute(0, 1, 4, 3, 2, 5)), dim=1)
@@ -101,4 +105,4 @@ class Renderer(object):
         faces = F.vertices_to_faces(vertices, faces)
         return rasterize(
             faces, textures, self.image_size, self.anti_aliasing, self.near, self.far, self.rasterizer_eps,
-            self.background_color)
+            self.background_color, reference_exact=self.reference_exact)

@@ -23,6 +23,10 @@ def _render_views(nr, vertices, textures, faces_idx, eyes, grad, S, fill_back):
     r = nr.Renderer()
     r.image_size, r.anti_aliasing, r.fill_back = S, False, fill_back
     r.eye = eyes
+    # rasterize.py:389 (the sampler reads the vertex depths of batch item 0 OF THE CALL) makes the reference's result depend
+    # on how the viewpoints are batched; sharding changes which viewpoint is "item 0".  The sharded and the single-rank
+    # run can only be compared with every item sampling with its own depths.
+    r.reference_exact = False
     V = eyes.shape[0]
     img = r.render(vertices[None].expand(V, -1, -1), faces_idx[None].expand(V, -1, -1), textures[None])
     (img * grad).sum().backward()
@@ -41,10 +45,7 @@ def _worker(rank, world, port, out_path):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    # rasterize.py:389 (the sampler reads the vertex depths of batch item 0 OF THE CALL) makes the reference's result depend
-    # on how the viewpoints are batched; sharding changes which viewpoint is "item 0".  The sharded and the single-rank
-    # run can only be compared with every item sampling with its own depths.
-    nr.set_reference_exact(False)
+
     F, S, ts, V_total = 20000, 256, 2, 6
     v_np, f_np = synthetic.sphere_mesh(F)
     faces_idx = torch.from_numpy(f_np).to(dev)
