@@ -81,6 +81,7 @@ struct BwdParams {
     int W;          // lines per strip (power of two)
     int w_log2, nstrips;
     int len_shift;  // scan length >> len_shift -> one of 32 sort buckets
+    int stage_fast; // even raster + 8-byte aligned maps: strips are staged with 8-byte loads
 #ifdef NR_B200_DEBUG_KNOBS
     int debug_skip; // ablation knob of experiment builds (NR_B200_ES_SKIP): 1 = no in-scan, 2 = no out-scan, 4 = no task processing
 #endif
@@ -316,6 +317,94 @@ __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThread
         }
         return q;
     };
+    // Fast path (two-line strips of an even raster, 8-byte aligned maps): a thread stages a 2 x 2 block of pixels (column
+    // strips: two image rows x the strip's two columns; row strips: one pixel pair of a line) with ONE 8-byte load per
+    // plane and image row instead of one 4-byte load per plane and pixel; with anti-aliasing the four pixels of a block
+    // share one texel of the pooled upstream gradient.
+    const bool stage_fast = p.stage_fast && nlines == 2 && W == 2;
+    if (stage_fast) {
+        const int H = S >> 1;
+        const int32_t* fimb = p.fim + (size_t)b * plane;
+        const float* rgbb = (kMode != 2) ? p.rgb + (size_t)b * 3 * plane : nullptr;
+        auto pooled = [&](const float* g, size_t pl, int row, int col) {
+            return 0.25f * __ldg(g + pl * (size_t)H * H + (size_t)(row >> 1) * H + (col >> 1));
+        };
+        struct Px2 { float A[2], g0[2], g1[2], g2[2], ga[2]; float4 c[2]; };
+        // two horizontally adjacent pixels (row, x), (row, x + 1) of the image, x even
+        auto load2 = [&](int row, int x) {
+            Px2 q;
+            const size_t o = (size_t)row * S + x;
+            const int2 fi = __ldg(reinterpret_cast<const int2*>(fimb + o));
+            const int f2[2] = {fi.x, fi.y};
+            float g[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // g0 g1 g2 ga
+            float col[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+            if (kMode != 2) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(rgbb + (size_t)c * plane + o));
+                    col[c][0] = v.x; col[c][1] = v.y;
+                    if (aa) {
+                        g[c][0] = g[c][1] = pooled(p.g_rgb, (size_t)b * 3 + c, row, x);
+                    } else {
+                        const float2 w = __ldg(reinterpret_cast<const float2*>(p.g_rgb + ((size_t)b * 3 + c) * plane + o));
+                        g[c][0] = w.x; g[c][1] = w.y;
+                    }
+                }
+            }
+            if (kMode != 1) {
+                if (aa) {
+                    g[3][0] = g[3][1] = pooled(p.g_alpha, (size_t)b, row, x);
+                } else {
+                    const float2 w = __ldg(reinterpret_cast<const float2*>(p.g_alpha + (size_t)b * plane + o));
+                    g[3][0] = w.x; g[3][1] = w.y;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const float alpha = f2[k] >= 0 ? 1.0f : 0.0f;
+                if (kMode == 2) {
+                    q.g0[k] = g[3][k]; q.g1[k] = q.g2[k] = q.ga[k] = 0.f;
+                    q.c[k] = make_float4(alpha, 0.f, 0.f, __int_as_float(f2[k]));
+                    q.A[k] = alpha * g[3][k];
+                } else {
+                    q.g0[k] = g[0][k]; q.g1[k] = g[1][k]; q.g2[k] = g[2][k]; q.ga[k] = g[3][k];
+                    q.c[k] = make_float4(col[0][k], col[1][k], col[2][k], __int_as_float(f2[k]));
+                    const float acc = (kMode == 3) ? alpha * g[3][k] : 0.0f;
+                    q.A[k] = __fmaf_rn(col[2][k], g[2][k], __fmaf_rn(col[1][k], g[1][k], __fmaf_rn(col[0][k], g[0][k], acc)));
+                }
+            }
+            return q;
+        };
+        auto put = [&](int line, int pp, const float A[2], const float g0[2], const float g1[2], const float g2[2], const float ga[2],
+                       const float4& ce, const float4& co) {
+            const size_t pi = (size_t)line * npair + pp;
+            P[pi] = make_float4(A[0], A[1], g0[0], g0[1]);
+            if (kMode != 2) Q[pi] = make_float4(g1[0], g1[1], g2[0], g2[1]);
+            if (kMode == 3) R[pi] = make_float2(ga[0], ga[1]);
+            ci[(size_t)line * Sp + 2 * pp] = ce;
+            ci[(size_t)line * Sp + 2 * pp + 1] = co;
+        };
+        if (axis == 0) {
+            // columns l0, l0 + 1; pair pp = raster rows y = 2pp, 2pp + 1 = image rows S-1-2pp and one above
+            for (int pp = tid; pp < npair; pp += kThreads) {
+                const int r0 = S - 1 - 2 * pp;
+                const Px2 a = load2(r0, l0), c = load2(r0 - 1, l0);  // a: y = 2pp (lines 0, 1), c: y = 2pp + 1
+#pragma unroll
+                for (int line = 0; line < 2; line++) {
+                    const float A[2] = {a.A[line], c.A[line]}, g0[2] = {a.g0[line], c.g0[line]}, g1[2] = {a.g1[line], c.g1[line]},
+                                g2[2] = {a.g2[line], c.g2[line]}, ga[2] = {a.ga[line], c.ga[line]};
+                    put(line, pp, A, g0, g1, g2, ga, a.c[line], c.c[line]);
+                }
+            }
+        } else {
+            // rows y = l0, l0 + 1; pair pp = columns 2pp, 2pp + 1 of one image row
+            for (int i = tid; i < 2 * npair; i += kThreads) {
+                const int line = i / npair, pp = i - line * npair;
+                const Px2 a = load2(S - 1 - (l0 + line), 2 * pp);
+                put(line, pp, a.A, a.g0, a.g1, a.g2, a.ga, a.c[0], a.c[1]);
+            }
+        }
+    } else
     for (int i = tid; i < nlines * npair; i += kThreads) {
         int line, pp;
         if (axis == 0) { line = i % nlines; pp = i / nlines; }   // columns: d0 = x, d1 = y
@@ -469,12 +558,24 @@ __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThread
                             p10 = nr::to_pixel(__ldg(nr::face_vertex_t<kIdx>(p.src, b, f, (e + 1) % 3) + axis), fS);
                 const int lo = max(__float2int_rz(fmaxf(ceilf(fminf(p00, p10)), 0.0f)), l0);
                 const int hi = min(__float2int_rz(fminf(fmaxf(p00, p10), (float)(S - 1))), lhi);
+                if (lo > hi) continue;
+                // Only what decides whether the slot is a task and how long it runs: the crossing (rasterize.py:567-573,
+                // slope hoisted out of the line loop) and the face_index_map gate of the out-scan (:604).  The full
+                // geometry of a task is set up once, by the lane that runs it (phase 3).  [0.583 -> 0.565 ms; without the
+                // gate in the sort key the batches get uneven and the kernel SLOWER, 0.641 ms]
+                const float p01 = nr::to_pixel(__ldg(nr::face_vertex_t<kIdx>(p.src, b, f, e) + (1 - axis)), fS),
+                            p11 = nr::to_pixel(__ldg(nr::face_vertex_t<kIdx>(p.src, b, f, (e + 1) % 3) + (1 - axis)), fS);
+                const bool lt = p00 < p10;
+                const int dir = (axis == 0) ? (lt ? -1 : 1) : (lt ? 1 : -1);
+                const float slope = __fdiv_rn(__fsub_rn(p11, p01), __fsub_rn(p10, p00));
                 for (int d0 = lo; d0 <= hi; d0++) {
                     const int line = d0 - l0;
-                    Task T;
-                    task_setup(f, e, line, T);
-                    if (!T.valid) continue;
-                    const int L = max(T.out_to - T.out_from + 1, 0) + 2 * max(T.in_to - T.in_from + 1, 0);
+                    const float d1_cross = __fmaf_rn(__fsub_rn((float)d0, p00), slope, p01);
+                    const int d1_in = __float2int_rz(dir > 0 ? floorf(d1_cross) : ceilf(d1_cross));
+                    const int d1_out = d1_in + dir;
+                    if (d1_in < 0 || d1_in >= S || d1_out < 0 || d1_out >= S) continue;
+                    const bool gate = __float_as_int(ci[(size_t)line * Sp + d1_in].w) == f;
+                    const int L = (gate ? (dir > 0 ? S - 1 - d1_in : d1_in) : 0) + 8;
                     const int bucket = min(L >> len_shift, 31);
                     const int rank = atomicAdd(&s_hist[bucket], 1);
                     const int t = atomicAdd(&s_ntask, 1);
@@ -966,6 +1067,7 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
         const int W = L.W;
         p.W = W; p.w_log2 = L.w_log2; p.nstrips = L.nstrips;
         p.len_shift = 3;
+        p.stage_fast = ((S & 1) == 0) && ((((uintptr_t)a->face_index_map | (uintptr_t)a->rgb_map | (uintptr_t)a->grad_rgb | (uintptr_t)a->grad_alpha) & 7) == 0);
 #ifdef NR_B200_DEBUG_KNOBS
         p.debug_skip = getenv("NR_B200_ES_SKIP") ? atoi(getenv("NR_B200_ES_SKIP")) : 0;
 #endif
