@@ -71,6 +71,7 @@ struct FwdParams {
     int* work_next;            // next (item, group) unit of k_raster_faces - 1 (memset to -1)
     int* any_big;              // -1 until some item has a big face
     int* big_list;             // [B,F]
+    float4* z0tab;             // [F] {z0, z1, z2, -} of EVERY face of batch item 0 (NR_TEX_Z_BATCH0 with RGB), else nullptr
     int32_t* fim;
     float* wmap;
     float* dmap;
@@ -246,6 +247,9 @@ __global__ void __launch_bounds__(kFaceWarps * 32, NR_FACES_MIN_CTAS) k_raster_f
         if (f < p.F) {
             float c[9];
             nr::load_face(p.src, b, f, c);
+            // rasterize.py:389: the sampler of every item reads the vertex depths of item 0 -- of drawn and culled faces
+            // alike -- so item 0's groups leave them in a compact table (one 16-byte load per pixel in k_resolve)
+            if (b == 0 && p.z0tab) p.z0tab[f] = make_float4(c[2], c[5], c[8], 0.0f);
             int xlo, xhi, ylo, yhi;
             if (face_pixel_box(c[0], c[1], c[3], c[4], c[6], c[7], S, xlo, xhi, ylo, yhi)) {
                 const float fS = (float)S;
@@ -400,18 +404,13 @@ __device__ __forceinline__ void blend_corners(const FwdParams& p, const nr::TexC
     }
 }
 
-// rasterize.py:389 -- the sampler's vertex depths come from batch item 0 (NR_TEX_Z_BATCH0), else from the winner's record
+// rasterize.py:389 -- the sampler's vertex depths come from batch item 0 (NR_TEX_Z_BATCH0: the table k_raster_faces
+// left), else from the winner's record
 __device__ __forceinline__ void sampler_depths(const FwdParams& p, int fn, const float4& cc, float& z0, float& z1, float& z2) {
     z0 = cc.y; z1 = cc.z; z2 = cc.w;
-    if (p.flags & NR_TEX_Z_BATCH0) {
-        if (p.src.idx == nullptr) {
-            const float* v0 = p.src.faces + (size_t)fn * 9;
-            z0 = __ldg(v0 + 2); z1 = __ldg(v0 + 5); z2 = __ldg(v0 + 8);
-        } else {
-            z0 = __ldg(nr::face_vertex(p.src, 0, fn, 0) + 2);
-            z1 = __ldg(nr::face_vertex(p.src, 0, fn, 1) + 2);
-            z2 = __ldg(nr::face_vertex(p.src, 0, fn, 2) + 2);
-        }
+    if (p.z0tab) {
+        const float4 z = __ldg(p.z0tab + fn);
+        z0 = z.x; z1 = z.y; z2 = z.z;
     }
 }
 
@@ -607,7 +606,7 @@ inline float float_ge(double d) {  // smallest float >= d
 }
 
 struct FwdLayout {
-    size_t off_cnt, off_zbuf, off_tab, off_list, total;
+    size_t off_cnt, off_zbuf, off_tab, off_list, off_z0, total;
 };
 // workspace = big-face counters | z-buffer (one memset covers both) | face records | big-face lists
 FwdLayout fwd_layout(int B, int F, int S) {
@@ -616,7 +615,8 @@ FwdLayout fwd_layout(int B, int F, int S) {
     L.off_zbuf = nr_align_up((size_t)(B + 2) * sizeof(int), 256);
     L.off_tab = L.off_zbuf + nr_align_up((size_t)B * S * S * sizeof(unsigned long long), 256);
     L.off_list = L.off_tab + nr_align_up((size_t)B * F * kRecWords * sizeof(float), 256);
-    L.total = L.off_list + nr_align_up((size_t)B * F * sizeof(int), 256);
+    L.off_z0 = L.off_list + nr_align_up((size_t)B * F * sizeof(int), 256);
+    L.total = L.off_z0 + nr_align_up((size_t)F * sizeof(float4), 256);
     return L;
 }
 
@@ -662,6 +662,7 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
     p.zbuf = (unsigned long long*)(wsb + L.off_zbuf);
     p.tab = (float4*)(wsb + L.off_tab);
     p.big_list = (int*)(wsb + L.off_list);
+    p.z0tab = ((flags & NR_RETURN_RGB) && (flags & NR_TEX_Z_BATCH0)) ? (float4*)(wsb + L.off_z0) : nullptr;
     p.fim = a->face_index_map; p.wmap = a->weight_map; p.dmap = a->depth_map; p.rgb = a->rgb_map; p.alpha = a->alpha_map;
     p.out_rgb = a->out_rgb; p.out_alpha = a->out_alpha; p.out_depth = a->out_depth;
     p.B = B; p.F = F; p.S = S; p.ts = ts; p.ngroups = (F + 31) / 32;
