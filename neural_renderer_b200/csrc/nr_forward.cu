@@ -57,6 +57,7 @@ constexpr int kOwnTable = 256;         // rows / fragments per pass whose owner 
 #define NR_RESOLVE_MIN_CTAS 8  // CTAs of 256 threads per SM the resolve pass is compiled for (32 registers: the pass is
                                // latency-bound on its dependent gathers, occupancy beats per-thread ILP -- measured)
 #endif
+constexpr int kResolveTileW = 32, kResolveTileH = 8;  // API pixels per k_resolve CTA (256 threads, 8 x 4 per warp)
 constexpr uint32_t kStageBytes = 32 * 1024;  // shared memory of a k_resolve CTA for staged texture cubes
 
 struct FwdParams {
@@ -489,7 +490,18 @@ __global__ void __launch_bounds__(256, kAA ? 5 : NR_RESOLVE_MIN_CTAS) k_resolve(
     float* wmap = p.wmap + (size_t)b * 3 * plane;
     float* rgb = want_rgb ? p.rgb + (size_t)b * 3 * plane : nullptr;
     float* alpha = p.alpha ? p.alpha + (size_t)b * plane : nullptr;
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    // Thread -> pixel map of the direct variants: a CTA of 256 threads covers a 32 x 8 tile of API pixels and every WARP an
+    // 8 x 4 block of it.  Faces are compact blobs (about 4 x 3 pixels at the headline shape), so a 2-D footprint meets a
+    // third of the distinct faces a 32 x 1 row segment meets -- and the gathers of the pass (texels, records) cost one
+    // L1 wavefront per request and distinct 128-byte line, i.e. per distinct face.  Stores and key loads become four
+    // 32-byte row segments per warp instead of one 128-byte segment: whole sectors, same DRAM traffic.
+    const int t_lane = threadIdx.x & 31, t_warp = threadIdx.x >> 5;
+    const int col2 = blockIdx.x * kResolveTileW + (t_warp & 3) * 8 + (t_lane & 7);
+    const int row2 = blockIdx.y * kResolveTileH + (t_warp >> 2) * 4 + (t_lane >> 3);
+    // (measured: 83 -> 74 us at the headline shape.  Anti-aliased quads are 2-D footprints already and lose 5 % with it, the
+    // texture / depth gradient kernels lose 3-5 %: those keep the row-major map.)
+    const bool tiled = !kStage && !kAA;
+    const int col = tiled ? col2 : (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (!kAA && kStage) {
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         const int row = blockIdx.y, yi = S - 1 - row;
@@ -553,8 +565,8 @@ __global__ void __launch_bounds__(256, kAA ? 5 : NR_RESOLVE_MIN_CTAS) k_resolve(
         rgb[o] = r; rgb[o + plane] = g; rgb[o + 2 * plane] = bl;
     } else if (!kAA) {
         // thread = one pixel of the IMAGE (row 0 = top): raster row yi = S - 1 - row
-        if (col >= S) return;
-        const int row = blockIdx.y, yi = S - 1 - row;
+        const int row = row2, yi = S - 1 - row;
+        if (col >= S || row >= S) return;
         const Shaded s = shade_pixel<kLit>(p, b, __ldg(zb + (uint32_t)yi * S + col), col, yi, bgr, bgg, bgb);
         const uint32_t o = (uint32_t)row * S + col;
         fim[o] = s.fim;
@@ -566,8 +578,8 @@ __global__ void __launch_bounds__(256, kAA ? 5 : NR_RESOLVE_MIN_CTAS) k_resolve(
         // thread = one pooled API pixel = one 2x2 quad of the raster
         const int H = S >> 1;
         const uint32_t oplane = (uint32_t)H * (uint32_t)H;
-        if (col >= H) return;
         const int orow = blockIdx.y;
+        if (col >= H) return;
         float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f, sd = 0.f;
         // the four pixels are shaded one after the other (keeps the register footprint of a single pixel) in image
         // order: top-left, top-right, bottom-left, bottom-right
@@ -708,8 +720,8 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
     {
         nr_internal::LaunchScope ls("k_resolve", stream);
         const int width = (flags & NR_ANTI_ALIASING) ? S / 2 : S;   // one thread per API pixel
-        const int bx = width >= 256 ? 256 : ((width + 31) / 32) * 32;
-        const dim3 grid((width + bx - 1) / bx, width, B);
+        int bx = width >= 256 ? 256 : ((width + 31) / 32) * 32;     // staged variant: a CTA = one row segment
+        dim3 grid((width + bx - 1) / bx, width, B);
         // Staging whole cubes with cp.async.bulk needs 16-byte aligned, 16-byte sized cubes; up to kStageBytes of
         // shared memory per CTA hold the cubes of the row's runs (the rest of the runs read global memory)
         const bool aa = (flags & NR_ANTI_ALIASING) != 0;
@@ -730,6 +742,10 @@ extern "C" int nr_b200_forward(const nr_b200_forward_args* a, void* cuda_stream)
         k_resolve<AA, TEX, LIT><<<grid, bx, smem, stream>>>(p, nslots);                             \
     } while (0)
 #define NR_RESOLVE_LIT(AA, TEX) do { if (lit) NR_RESOLVE(AA, TEX, true); else NR_RESOLVE(AA, TEX, false); } while (0)
+        if (!stage && !aa) {  // direct variant: 32 x 8 pixel tiles
+            bx = 256;
+            grid = dim3((width + kResolveTileW - 1) / kResolveTileW, (width + kResolveTileH - 1) / kResolveTileH, B);
+        }
         if (aa) NR_RESOLVE_LIT(true, 0);
         else if (stage) NR_RESOLVE_LIT(false, 1);
         else NR_RESOLVE_LIT(false, 0);
