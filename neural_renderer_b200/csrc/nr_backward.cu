@@ -131,20 +131,65 @@ constexpr int kBinSmemStrips = 2048;  // strips (+1 wide slot) per axis whose co
 // faces hit the same few strips: native shared-memory integer atomics instead of contended global ones); the CTA then
 // touches every non-empty global counter / cursor ONCE to publish its count (kFill = false) or to reserve its range of
 // the list (kFill = true), and the faces are written at reserved base + local rank.
+// The two launches also do what used to be launches of their own (4 small latency-bound kernels -> 2): the counting
+// pass computes the faces' pixel boxes itself (k_face_bbox), and every CTA of the fill pass scans its item's 2 x
+// (nstrips + 1) counters in shared memory (k_strip_scan) -- CTA 0 of an item leaves the offsets for the edge scan.
 template <bool kFill>
-__global__ void __launch_bounds__(256) k_strip_bin(const uint2* __restrict__ bbox, int F, int w_log2, int nstrips,
-                                                   int* __restrict__ cnt, const int* __restrict__ off,
-                                                   int* __restrict__ cursor, int* __restrict__ list) {
-    extern __shared__ int s_bin[];  // [2][nstrips + 1] local counts, then (fill) [2][nstrips + 1] reserved bases
+__global__ void __launch_bounds__(256) k_strip_bin(const nr::FaceSrc src, uint2* __restrict__ bbox, int F, int S, int w_log2,
+                                                   int nstrips, int* __restrict__ cnt, int* __restrict__ off,
+                                                   int* __restrict__ cursor, int* __restrict__ list, long long seg_stride) {
+    extern __shared__ int s_bin[];  // [2][nstrips + 1] local counts, then (fill) [2][nstrips + 1] offsets / reserved bases
+    __shared__ int s_warp[8];
     const int b = blockIdx.y;
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int f = blockIdx.x * blockDim.x + tid;
     const int nslots = 2 * (nstrips + 1);
+    const size_t gbase = (size_t)b * nslots;
     int* s_cnt = s_bin;
     int* s_base = s_bin + nslots;
-    for (int i = threadIdx.x; i < nslots; i += blockDim.x) s_cnt[i] = 0;
+    for (int i = tid; i < nslots; i += blockDim.x) {
+        s_cnt[i] = 0;
+        if (kFill) s_base[i] = cnt[gbase + i];
+    }
     __syncthreads();
     uint2 bb = make_uint2(pack16(1, 0), pack16(1, 0));
-    if (f < F) bb = __ldg(bbox + (size_t)b * F + f);
+    if (f < F) {
+        if (kFill) {
+            bb = __ldg(bbox + (size_t)b * F + f);
+        } else {
+            const float *v0 = nr::face_vertex(src, b, f, 0), *v1 = nr::face_vertex(src, b, f, 1), *v2 = nr::face_vertex(src, b, f, 2);
+            int xlo, xhi, ylo, yhi;
+            if (face_pixel_box(__ldg(v0), __ldg(v0 + 1), __ldg(v1), __ldg(v1 + 1), __ldg(v2), __ldg(v2 + 1), S, xlo, xhi, ylo, yhi))
+                bb = make_uint2(pack16(xlo, xhi), pack16(ylo, yhi));
+            bbox[(size_t)b * F + f] = bb;
+        }
+    }
+    if (kFill) {
+        // exclusive scan of each axis' counters; segment (item, axis) owns list entries [seg * seg_stride, ...)
+        for (int axis = 0; axis < 2; axis++) {
+            int* a = s_base + axis * (nstrips + 1);
+            const int n = nstrips + 1, K = (n + 255) >> 8;
+            int sum = 0;
+            for (int k = 0; k < K; k++) { const int i = tid * K + k; if (i < n) sum += a[i]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_warp[tid >> 5] = incl;
+            __syncthreads();
+            int run = (int)(((long long)b * 2 + axis) * seg_stride) + incl - sum;
+            for (int w = 0; w < (tid >> 5); w++) run += s_warp[w];
+            for (int k = 0; k < K; k++) {
+                const int i = tid * K + k;
+                if (i < n) { const int v = a[i]; a[i] = run; run += v; }
+            }
+            __syncthreads();
+        }
+        if (blockIdx.x == 0)
+            for (int i = tid; i < nslots; i += blockDim.x) off[gbase + i] = s_base[i];
+    }
     const bool active = unpack_lo(bb.x) <= unpack_hi(bb.x);  // culled faces carry an empty box
     int slot0[2], nslot[2];
     int rank[2][kWideStrips];
@@ -162,12 +207,11 @@ __global__ void __launch_bounds__(256) k_strip_bin(const uint2* __restrict__ bbo
         }
     }
     __syncthreads();
-    const size_t gbase = (size_t)b * nslots;
-    for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
+    for (int i = tid; i < nslots; i += blockDim.x) {
         const int c = s_cnt[i];
         if (c == 0) continue;
         if (!kFill) atomicAdd(cnt + gbase + i, c);
-        else s_base[i] = off[gbase + i] + atomicAdd(cursor + gbase + i, c);
+        else s_base[i] += atomicAdd(cursor + gbase + i, c);
     }
     if (!kFill) return;
     __syncthreads();
@@ -1084,14 +1128,8 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
     // K5 runs when an rgb or alpha gradient exists (rasterize.py:523); without upstream gradients it contributes 0
     const bool need_scan = (rgb && p.g_rgb) || (alpha && p.g_alpha);
     if (need_scan) {
-        const int nchunks = (F + kChunk - 1) / kChunk, ngroups = (F + kGroup - 1) / kGroup;
         uint2* bbox = (uint2*)a->workspace;
         uint2* cbox = (uint2*)((char*)a->workspace + nr_align_up((size_t)B * F * sizeof(uint2), 256));
-        {
-            nr_internal::LaunchScope ls("k_face_bbox", stream);
-            k_face_bbox<<<dim3(nchunks, B), kChunk, 0, stream>>>(src, F, S, ngroups, bbox, cbox);
-        }
-        p.bbox = bbox; p.chunk_bbox = cbox; p.nchunks = ngroups;
         const bool use_rgb = rgb && p.g_rgb, use_alpha = alpha && p.g_alpha;
         const int rec_bytes = (use_rgb && use_alpha) ? 36 : 32;
         const BinLayout L = bin_layout(B, F, S, (rgb && alpha) ? 36 : 32);  // same strip width as the workspace query
@@ -1119,21 +1157,40 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
             if (getenv("NR_B200_BIN_GLOBAL")) bin_smem = false;
 #endif
             const size_t bin_bytes = (size_t)4 * (nstrips + 1) * sizeof(int);
-            {
-                nr_internal::LaunchScope ls("k_strip_bin", stream);
-                if (bin_smem) k_strip_bin<false><<<g, 256, bin_bytes, stream>>>(bbox, F, L.w_log2, nstrips, cnt, nullptr, nullptr, nullptr);
-                else k_strip_bin_global<false><<<g, 256, 0, stream>>>(bbox, F, L.w_log2, nstrips, cnt, nullptr, nullptr, nullptr);
-            }
-            {
-                nr_internal::LaunchScope ls("k_strip_scan", stream);
-                k_strip_scan<<<B * 2, 256, 0, stream>>>(cnt, off, nstrips + 1, (long long)F * kWideStrips);
-            }
-            {
-                nr_internal::LaunchScope ls("k_strip_bin", stream);
-                if (bin_smem) k_strip_bin<true><<<g, 256, bin_bytes, stream>>>(bbox, F, L.w_log2, nstrips, cnt, off, cursor, list);
-                else k_strip_bin_global<true><<<g, 256, 0, stream>>>(bbox, F, L.w_log2, nstrips, cnt, off, cursor, list);
+            const long long seg_stride = (long long)F * kWideStrips;
+            if (bin_smem) {
+                static nr_internal::SmemOptIn optin_count, optin_fill;
+                if (optin_count.ensure(k_strip_bin<false>, bin_bytes) != cudaSuccess || optin_fill.ensure(k_strip_bin<true>, bin_bytes) != cudaSuccess)
+                    return NR_ERR_CUDA;
+                {
+                    nr_internal::LaunchScope ls("k_strip_bin", stream);
+                    k_strip_bin<false><<<g, 256, bin_bytes, stream>>>(src, bbox, F, S, L.w_log2, nstrips, cnt, nullptr, nullptr, nullptr, seg_stride);
+                }
+                {
+                    nr_internal::LaunchScope ls("k_strip_bin", stream);
+                    k_strip_bin<true><<<g, 256, bin_bytes, stream>>>(src, bbox, F, S, L.w_log2, nstrips, cnt, off, cursor, list, seg_stride);
+                }
+            } else {
+                const int nchunks = (F + kChunk - 1) / kChunk, ngroups = (F + kGroup - 1) / kGroup;
+                {
+                    nr_internal::LaunchScope ls("k_face_bbox", stream);
+                    k_face_bbox<<<dim3(nchunks, B), kChunk, 0, stream>>>(src, F, S, ngroups, bbox, cbox);
+                }
+                {
+                    nr_internal::LaunchScope ls("k_strip_bin", stream);
+                    k_strip_bin_global<false><<<g, 256, 0, stream>>>(bbox, F, L.w_log2, nstrips, cnt, nullptr, nullptr, nullptr);
+                }
+                {
+                    nr_internal::LaunchScope ls("k_strip_scan", stream);
+                    k_strip_scan<<<B * 2, 256, 0, stream>>>(cnt, off, nstrips + 1, seg_stride);
+                }
+                {
+                    nr_internal::LaunchScope ls("k_strip_bin", stream);
+                    k_strip_bin_global<true><<<g, 256, 0, stream>>>(bbox, F, L.w_log2, nstrips, cnt, off, cursor, list);
+                }
             }
         }
+        p.bbox = bbox;
         p.strip_cnt = cnt; p.strip_off = off; p.strip_list = list;
         int rc;
         if (use_rgb && use_alpha) rc = launch_edge_scan<3>(p, nstrips, smem, stream);
