@@ -22,8 +22,33 @@ __device__ __forceinline__ int unpack_lo(uint32_t v) { return (int)(short)(v & 0
 __device__ __forceinline__ int unpack_hi(uint32_t v) { return (int)(short)(v >> 16); }
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 
+// How far outside its vertex box a face can still pass the reference's three edge tests (rasterize.py:309-311).
+// Each test compares two fp32 products of fp32 differences (three roundings a side), so a pixel centre p is accepted
+// by edge k whenever its exact signed distance to that edge's line is >= -delta, delta <= 4.4 u D in the rasterizer's
+// input coordinates (u = 2^-24, D = sqrt(2) + max |vertex| bounds |p - v_k|).  The accepted set is therefore inside
+// the triangle grown by delta along every edge normal, whose corners sit delta / sin(theta_v / 2) <= 2 delta L^2 / |det|
+// beyond the vertices (theta_v the interior angle, L the longest edge, det twice the area).  For an ordinary face that
+// is 1e-6 of a pixel; for a needle whose long edges meet at 1e-4 rad it is more than a pixel, and such a needle DOES win
+// pixels beyond its tip in the reference (tests/test_gpu_parity.py::test_needle_faces).  The margin below carries a
+// 3.6x safety factor for the rounding of L^2 / |det| itself and is capped at kThinMarginCap pixels: thinner than about
+// 7e-5 rad (or exactly collinear, which never wins: every weight is NaN) the bound is not attained any more.
+constexpr float kThinMarginCap = 8.0f;
+
+__device__ __forceinline__ float thin_face_margin(float x0, float y0, float x1, float y1, float x2, float y2, float fS) {
+    const float ex0 = __fsub_rn(x1, x0), ey0 = __fsub_rn(y1, y0), ex1 = __fsub_rn(x2, x1), ey1 = __fsub_rn(y2, y1);
+    const float ex2 = __fsub_rn(x0, x2), ey2 = __fsub_rn(y0, y2);
+    const float l2 = fmaxf(__fmaf_rn(ex0, ex0, ey0 * ey0), fmaxf(__fmaf_rn(ex1, ex1, ey1 * ey1), __fmaf_rn(ex2, ex2, ey2 * ey2)));
+    const float det = fabsf(__fmaf_rn(ex0, ey1, -(ey0 * ex1)));
+    const float m = fmaxf(fmaxf(fabsf(x0), fabsf(y0)), fmaxf(fmaxf(fabsf(x1), fabsf(y1)), fmaxf(fabsf(x2), fabsf(y2))));
+    const float D = 1.4143f * (1.0f + m);
+    const float ext = __fdividef(16.0f * 5.9604645e-8f * D * fS * l2, det);  // pixels; inf / NaN for a collinear face
+    return (ext < kThinMarginCap) ? ext : kThinMarginCap;
+}
+
 // Conservative pixel box of a face; false = the face can never win a pixel (back-facing, rasterize.py:252/:306/:540, a
-// non-finite x/y, or entirely off screen).
+// non-finite x/y, or entirely off screen).  kCoverage: the box must hold every pixel the forward's edge tests can
+// accept (adds the thin-face margin); the backward only needs the columns / rows its edge scan can start from.
+template <bool kCoverage = false>
 __device__ __forceinline__ bool face_pixel_box(float x0, float y0, float x1, float y1, float x2, float y2, int S, int& xlo,
                                                int& xhi, int& ylo, int& yhi) {
     const bool finite = isfinite(x0) && isfinite(y0) && isfinite(x1) && isfinite(y1) && isfinite(x2) && isfinite(y2);
@@ -33,8 +58,9 @@ __device__ __forceinline__ bool face_pixel_box(float x0, float y0, float x1, flo
     const float pxmin = nr::to_pixel(fminf(x0, fminf(x1, x2)), fS), pxmax = nr::to_pixel(fmaxf(x0, fmaxf(x1, x2)), fS);
     const float pymin = nr::to_pixel(fminf(y0, fminf(y1, y2)), fS), pymax = nr::to_pixel(fmaxf(y0, fmaxf(y1, y2)), fS);
     const float lim = (float)(S - 1);
-    const float fx0 = fmaxf(floorf(pxmin - kBoxMargin), 0.0f), fx1 = fminf(ceilf(pxmax + kBoxMargin), lim);
-    const float fy0 = fmaxf(floorf(pymin - kBoxMargin), 0.0f), fy1 = fminf(ceilf(pymax + kBoxMargin), lim);
+    const float margin = kCoverage ? kBoxMargin + thin_face_margin(x0, y0, x1, y1, x2, y2, fS) : kBoxMargin;
+    const float fx0 = fmaxf(floorf(pxmin - margin), 0.0f), fx1 = fminf(ceilf(pxmax + margin), lim);
+    const float fy0 = fmaxf(floorf(pymin - margin), 0.0f), fy1 = fminf(ceilf(pymax + margin), lim);
     if (!(fx0 <= fx1 && fy0 <= fy1)) return false;
     xlo = (int)fx0; xhi = (int)fx1; ylo = (int)fy0; yhi = (int)fy1;
     return true;

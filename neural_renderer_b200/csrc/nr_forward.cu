@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kFaceWarps * 32, NR_FACES_MIN_CTAS) k_raster_f
             // alike -- so item 0's groups leave them in a compact table (one 16-byte load per pixel in k_resolve)
             if (b == 0 && p.z0tab) p.z0tab[f] = make_float4(c[2], c[5], c[8], 0.0f);
             int xlo, xhi, ylo, yhi;
-            if (face_pixel_box(c[0], c[1], c[3], c[4], c[6], c[7], S, xlo, xhi, ylo, yhi)) {
+            if (face_pixel_box<true>(c[0], c[1], c[3], c[4], c[6], c[7], S, xlo, xhi, ylo, yhi)) {
                 const float fS = (float)S;
                 float inv[9];
                 nr::face_inverse(nr::to_pixel(c[0], fS), nr::to_pixel(c[1], fS), nr::to_pixel(c[3], fS), nr::to_pixel(c[4], fS),
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256) k_raster_big(const __grid_constant__ FwdP
             float c[9];
             nr::load_face(p.src, b, f, c);  // warp-uniform
             int xlo, xhi, ylo, yhi;
-            if (!face_pixel_box(c[0], c[1], c[3], c[4], c[6], c[7], S, xlo, xhi, ylo, yhi)) continue;
+            if (!face_pixel_box<true>(c[0], c[1], c[3], c[4], c[6], c[7], S, xlo, xhi, ylo, yhi)) continue;
             xlo = max(xlo, tx0); xhi = min(xhi, tx1); ylo = max(ylo, ty0); yhi = min(yhi, ty1);
             if (xlo > xhi || ylo > yhi) continue;
             // the face sits in slot 0 of the warp's scratch; every lane rasterizes rows of that one face

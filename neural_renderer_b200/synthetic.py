@@ -78,3 +78,52 @@ def triangle_soup(batch_size, num_faces, seed=0, size=(0.05, 0.5), z_range=(1.0,
             dst = rng.integers(0, num_faces, size=src.shape[0])
             f[b, dst] = f[b, src]
     return f
+
+
+def needle_faces(batch_size, num_faces, image_size, seed=0, thin=(1e-7, 1e-4), z_range=(1.0, 3.0)):
+    """Front-facing needles that win a pixel BEYOND their tip: the tip sits a fraction of a pixel in front of a pixel
+    centre on the needle's axis and the two long edges meet at `thin` (half width / length, log-uniform).  Candidates are
+    drawn until the reference's own fp32 edge tests (rasterize.py:306-311, replayed here in numpy float32) accept that
+    pixel centre -- a pixel outside the box of the three vertices (about one candidate in a thousand).  Stress for the
+    conservative pixel box of the forward pass (nr_bbox.cuh: thin_face_margin)."""
+    rng = np.random.default_rng(seed)
+    S = image_size
+    f32 = np.float32
+    centres = ((2 * np.arange(S) + 1 - S) / S).astype(f32)
+    out = np.empty((batch_size, num_faces, 3, 3), dtype=f32)
+    for b in range(batch_size):
+        kept = []
+        while len(kept) < num_faces:
+            n = 200000
+            cx = centres[rng.integers(S // 8, S - S // 8, size=n)].astype(np.float64)
+            cy = centres[rng.integers(S // 8, S - S // 8, size=n)].astype(np.float64)
+            ang = rng.uniform(0, 2 * np.pi, size=n)
+            dx, dy = np.cos(ang), np.sin(ang)
+            back = rng.uniform(0.05, 1.5, size=n) * 2.0 / S
+            ax, ay = cx - dx * back, cy - dy * back
+            length = rng.uniform(0.2, 0.8, size=n)
+            half = length * np.exp(rng.uniform(np.log(thin[0]), np.log(thin[1]), size=n))
+            bx, by = ax - dx * length, ay - dy * length
+            v = np.stack([np.stack([ax, ay], -1), np.stack([bx - dy * half, by + dx * half], -1),
+                          np.stack([bx + dy * half, by - dx * half], -1)], 1).astype(f32)  # [n,3,2]
+            # front-facing in the reference's sense (rasterize.py:306): swap two vertices if not
+            back_side = (v[:, 2, 1] - v[:, 0, 1]) * (v[:, 1, 0] - v[:, 0, 0]) < (v[:, 1, 1] - v[:, 0, 1]) * (v[:, 2, 0] - v[:, 0, 0])
+            v[back_side] = v[back_side][:, [0, 2, 1]]
+            back_side = (v[:, 2, 1] - v[:, 0, 1]) * (v[:, 1, 0] - v[:, 0, 0]) < (v[:, 1, 1] - v[:, 0, 1]) * (v[:, 2, 0] - v[:, 0, 0])
+            xp, yp = cx.astype(f32), cy.astype(f32)
+            ok = ~back_side
+            for k in range(3):
+                k1 = (k + 1) % 3
+                ok &= ~((yp - v[:, k, 1]) * (v[:, k1, 0] - v[:, k, 0]) < (xp - v[:, k, 0]) * (v[:, k1, 1] - v[:, k, 1]))
+            # the aimed pixel must lie outside the vertices' pixel box
+            px, py = 0.5 * (v[:, :, 0] * S + S - 1), 0.5 * (v[:, :, 1] * S + S - 1)
+            ix, iy = 0.5 * (xp * S + S - 1), 0.5 * (yp * S + S - 1)
+            outside = (ix > np.ceil(px.max(1) + 1 / 256)) | (ix < np.floor(px.min(1) - 1 / 256)) | \
+                      (iy > np.ceil(py.max(1) + 1 / 256)) | (iy < np.floor(py.min(1) - 1 / 256))
+            for i in np.nonzero(ok & outside)[0]:
+                kept.append(v[i])
+                if len(kept) == num_faces:
+                    break
+        z = rng.uniform(z_range[0], z_range[1], size=(num_faces, 3, 1)).astype(f32)
+        out[b] = np.concatenate([np.stack(kept), z], axis=-1)
+    return out

@@ -121,6 +121,45 @@ def test_forward_backward_vs_reference_kernels(case):
         assert rel_err(np_(got["grad_tex"]), np_(gt)) <= TOL, "grad_textures"
 
 
+def _outside_box_wins(fim, faces, S):
+    """Pixels whose winning face does not contain them in the pixel box of its three vertices (+- 1/256 px)."""
+    n = 0
+    for b in range(fim.shape[0]):
+        ys, xs = np.nonzero(fim[b] >= 0)
+        v = faces[b, fim[b, ys, xs]]  # [n,3,3]
+        px, py = 0.5 * (v[:, :, 0] * S + S - 1), 0.5 * (v[:, :, 1] * S + S - 1)
+        n += int(((xs > np.ceil(px.max(1) + 1 / 256)) | (xs < np.floor(px.min(1) - 1 / 256)) |
+                  (ys > np.ceil(py.max(1) + 1 / 256)) | (ys < np.floor(py.min(1) - 1 / 256))).sum())
+    return n
+
+
+@pytest.mark.parametrize("flags", [(0, 1, 0), (1, 1, 1)], ids=["alpha", "all"])
+def test_needle_faces(flags):
+    """Needles whose long edges meet at 1e-7 .. 1e-4 rad win pixels BEYOND their tip in the reference (the fp32 edge
+    tests of rasterize.py:309-311 accept a pixel centre on the needle's axis): the forward's conservative pixel box has
+    to reach them (nr_bbox.cuh thin_face_margin).  Half of the faces are ordinary triangles that compete for the pixels."""
+    import refhost
+    from neural_renderer_b200 import synthetic
+    image_size, F, ts, B, near, far, eps = 64, 200, 4, 3, 0.1, 100, 1e-4
+    if not refhost.available(image_size, F, ts if flags[0] else 0, near, far, eps, *flags):
+        pytest.skip("reference kernels for this configuration were not built (oracle/build_ref.py)")
+    faces = synthetic.triangle_soup(B, F, seed=11, z_range=(1.5, 3.0))
+    faces[:, : F // 2] = synthetic.needle_faces(B, F // 2, image_size, seed=5)
+    tex = synthetic.random_textures(B, F, ts, seed=3)
+    dev = torch.device("cuda")
+    bg = (0.1, 0.3, 0.5)
+    ref = refhost.rasterize_rgbad(torch.from_numpy(faces).to(dev), torch.from_numpy(tex).to(dev) if flags[0] else None,
+                                  image_size, False, near, far, eps, bg, *flags)
+    ref_fim = np_(ref.fn.face_index_map)
+    assert _outside_box_wins(ref_fim, faces, image_size) >= 20, "the case does not exercise the thin-face margin"
+    got = _run_product(faces, tex, image_size, False, near, far, eps, bg, flags)
+    assert torch.equal(got["fim"].flip(1), ref.fn.face_index_map), "face_index_map differs"
+    assert torch.equal(got["wmap"].permute(0, 2, 3, 1).flip(1), ref.fn.weight_map), "weight_map not bit-exact"
+    for k in ("rgb", "alpha", "depth"):
+        if ref[k] is not None:
+            assert int((got[k] != ref[k]).sum().item()) == 0, k
+
+
 @pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("tiny_all", "soup_all", "npot_all", "aa_all")],
                          ids=lambda c: c[0])
 def test_forward_backward_vs_cpu_oracle(case):

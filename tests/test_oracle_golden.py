@@ -149,3 +149,30 @@ def test_row_coverage_is_one_interval_in_fp32():
                 inside &= ~out
             runs = (inside[:, 1:] != inside[:, :-1]).sum(axis=1) + inside[:, 0] + inside[:, -1]
             assert runs.max() <= 2                                                      # covered pixels: one interval per row
+
+
+def test_needles_win_pixels_beyond_their_vertex_box_and_the_margin_covers_them():
+    """What the forward's thin-face margin (csrc/nr_bbox.cuh: thin_face_margin) is for, on the CPU oracle: needles whose
+    long edges meet at 1e-7 .. 1e-4 rad pass the reference's fp32 edge tests (rasterize.py:309-311) at a pixel centre
+    beyond their tip and WIN it; the margin formula, replayed in numpy, reaches every such pixel."""
+    import nr_oracle as o
+    from neural_renderer_b200 import synthetic
+    S, F = 64, 100
+    faces = synthetic.needle_faces(1, F, S, seed=3)
+    r = o.OracleRasterize(S, 0.1, 100, 1e-4, (0, 0, 0), return_alpha=True)
+    r.forward(faces)
+    fim = r.face_index_map[0]
+    ys, xs = np.nonzero(fim >= 0)
+    v = faces[0, fim[ys, xs]]
+    px, py = 0.5 * (v[:, :, 0] * S + S - 1), 0.5 * (v[:, :, 1] * S + S - 1)
+    over = np.maximum.reduce([xs - px.max(1), px.min(1) - xs, ys - py.max(1), py.min(1) - ys])  # pixels beyond the vertices
+    outside = over > 1.0 / 256
+    assert outside.sum() >= F // 2
+    e = np.stack([v[:, 1, :2] - v[:, 0, :2], v[:, 2, :2] - v[:, 1, :2], v[:, 0, :2] - v[:, 2, :2]], 1).astype(np.float32)
+    l2 = (e ** 2).sum(-1).max(1)
+    det = np.abs(e[:, 0, 0] * e[:, 1, 1] - e[:, 0, 1] * e[:, 1, 0])
+    D = 1.4143 * (1 + np.abs(v[:, :, :2]).max((1, 2)))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ext = 16 * 2.0 ** -24 * D * S * l2 / det
+    margin = 1.0 / 256 + np.where(ext < 8.0, ext, 8.0)  # NaN / inf -> the cap, like the kernel
+    assert (over[outside] <= 0.5 * margin[outside]).all()
