@@ -88,6 +88,7 @@ struct BwdParams {
     int w_log2, nstrips;
     int len_shift;  // scan length >> len_shift -> one of 32 sort buckets
     int stage_fast; // even raster + 8-byte aligned maps: strips are staged with 8-byte loads
+    int col_smem;   // the strip keeps the pixels' colours in shared memory (rasters up to kColSmemMaxS)
 #ifdef NR_B200_DEBUG_KNOBS
     int debug_skip; // ablation knob of experiment builds (NR_B200_ES_SKIP): 1 = no in-scan, 2 = no out-scan, 4 = no task processing
 #endif
@@ -306,10 +307,13 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f
 //   P[pp] = {A_e, A_o, g0_e, g0_o}   A = sum_c I_c * g_c (+ alpha * g_alpha): the scan evaluates the reference's
 //   Q[pp] = {g1_e, g1_o, g2_e, g2_o}     diff_grad = sum_c (I_c - ref_c) * g_c  as  A - sum_c ref_c * g_c
 //   R[pp] = {ga_e, ga_o}             only when both rgb and alpha gradients exist (kMode == 3)
-//   ci[i] = {I0, I1, I2, fim}        colours and face index per pixel: task set-up and the short in-scan only
+//   ci[i] = {I0, I1, I2, fim}        colours and face index per pixel: task set-up and the short in-scan only (kCol)
+//   fs[i] = fim                      face index only (!kCol): larger rasters keep 20 instead of 32 bytes per pixel in
+//                                    shared memory (8 instead of 5 CTAs per SM at raster 512) and fetch the two
+//                                    reference colours of a task from the global rgb map (L2 hits) when it is set up
 // kMode: 1 = rgb, 2 = alpha only (g0 = g_alpha, I0 = alpha), 3 = rgb + alpha
 //@phase prologue
-template <int kMode, int kThreads, bool kIdx>
+template <int kMode, int kThreads, bool kIdx, bool kCol>
 __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThreads / 8) k_edge_scan(const __grid_constant__ BwdParams p) {
     constexpr int kFaceQueue = 2 * kThreads, kTaskCap = 8 * kThreads;
     static_assert(kFaceQueue <= 512 && kTaskCap <= 4096, "task word layout");
@@ -318,8 +322,9 @@ __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThread
     const int Sp = (S + 1) & ~1, npair = Sp >> 1;
     float4* P = reinterpret_cast<float4*>(smem_raw);
     float4* Q = P + (size_t)W * npair;
-    float4* ci = Q + (size_t)W * npair;
-    float2* R = reinterpret_cast<float2*>(ci + (size_t)W * Sp);
+    float4* ci = Q + (size_t)W * npair;                  // kCol
+    int* fs = reinterpret_cast<int*>(Q + (size_t)W * npair);  // !kCol (same place)
+    float2* R = kCol ? reinterpret_cast<float2*>(ci + (size_t)W * Sp) : reinterpret_cast<float2*>(fs + (size_t)W * Sp);
     __shared__ int s_faceq[kFaceQueue];
     __shared__ uint32_t s_tmp[kTaskCap];     // unsorted tasks: q<<23 | e<<21 | line<<17 | bucket<<12 | rank
     __shared__ uint16_t s_sorted[kTaskCap];  // tasks ordered by descending scan length: q<<6 | e<<4 | line
@@ -431,8 +436,12 @@ __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThread
             P[pi] = make_float4(A[0], A[1], g0[0], g0[1]);
             if (kMode != 2) Q[pi] = make_float4(g1[0], g1[1], g2[0], g2[1]);
             if (kMode == 3) R[pi] = make_float2(ga[0], ga[1]);
-            ci[(size_t)line * Sp + 2 * pp] = ce;
-            ci[(size_t)line * Sp + 2 * pp + 1] = co;
+            if (kCol) {
+                ci[(size_t)line * Sp + 2 * pp] = ce;
+                ci[(size_t)line * Sp + 2 * pp + 1] = co;
+            } else {
+                *reinterpret_cast<int2*>(fs + (size_t)line * Sp + 2 * pp) = make_int2(__float_as_int(ce.w), __float_as_int(co.w));
+            }
         };
         if (axis == 0) {
             // columns l0, l0 + 1; pair pp = raster rows y = 2pp, 2pp + 1 = image rows S-1-2pp and one above
@@ -464,8 +473,12 @@ __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThread
         P[pi] = make_float4(e.A, o.A, e.g0, o.g0);
         if (kMode != 2) Q[pi] = make_float4(e.g1, o.g1, e.g2, o.g2);
         if (kMode == 3) R[pi] = make_float2(e.ga, o.ga);
-        ci[(size_t)line * Sp + 2 * pp] = e.c;
-        ci[(size_t)line * Sp + 2 * pp + 1] = o.c;
+        if (kCol) {
+            ci[(size_t)line * Sp + 2 * pp] = e.c;
+            ci[(size_t)line * Sp + 2 * pp + 1] = o.c;
+        } else {
+            *reinterpret_cast<int2*>(fs + (size_t)line * Sp + 2 * pp) = make_int2(__float_as_int(e.c.w), __float_as_int(o.c.w));
+        }
     }
     if (tid < 32) s_hist[tid] = 0;
     if (tid == 0) { s_nface = 0; s_ntask = 0; s_next = 0; }
@@ -474,6 +487,21 @@ __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThread
     const uint2* bbox = p.bbox + (size_t)b * p.F;
     const float fS = (float)S;
     const int lhi = l0 + nlines - 1;
+    // face index / {I0, I1, I2, fim} of pixel d1 of a line of the strip
+    auto fim_at = [&](int line, int d1) -> int {
+        return kCol ? __float_as_int(ci[(size_t)line * Sp + d1].w) : fs[(size_t)line * Sp + d1];
+    };
+    auto colour_at = [&](int line, int d1) -> float4 {
+        if (kCol) return ci[(size_t)line * Sp + d1];
+        const int fi = fs[(size_t)line * Sp + d1];
+        float4 c = make_float4(fi >= 0 ? 1.0f : 0.0f, 0.0f, 0.0f, __int_as_float(fi));  // kMode 2: I0 = alpha
+        if (kMode != 2) {
+            const int x = (axis == 0) ? l0 + line : d1, y = (axis == 0) ? d1 : l0 + line;
+            const float* rm = p.rgb + (size_t)b * 3 * plane + (size_t)(S - 1 - y) * S + x;
+            c.x = __ldg(rm); c.y = __ldg(rm + plane); c.z = __ldg(rm + 2 * plane);
+        }
+        return c;
+    };
 
     //@phase task_setup (inlined into 2b and 3)
     // Geometry of one (face, edge, line) scan, evaluated exactly as rasterize.py:545-609 / :662-672 does.
@@ -514,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThread
         T.k0 = __fdiv_rn(len, __fsub_rn(p10, fd0)) * p.two_over_S;
         T.k1 = __fdiv_rn(len, __fsub_rn(fd0, p00)) * p.two_over_S;
         // out-scan: from the outside pixel to the image border, only if the inside pixel shows this face
-        if (__float_as_int(ci[(size_t)line * Sp + T.d1_in].w) == f) {
+        if (fim_at(line, T.d1_in) == f) {
             const int lim = (T.dir > 0) ? S - 1 : 0;
             T.out_from = max(min(T.d1_out, lim), 0);
             T.out_to = min(max(T.d1_out, lim), S - 1);
@@ -624,7 +652,7 @@ __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThread
                     const int d1_in = __float2int_rz(dir > 0 ? floorf(d1_cross) : ceilf(d1_cross));
                     const int d1_out = d1_in + dir;
                     if (d1_in < 0 || d1_in >= S || d1_out < 0 || d1_out >= S) continue;
-                    const bool gate = __float_as_int(ci[(size_t)line * Sp + d1_in].w) == f;
+                    const bool gate = fim_at(line, d1_in) == f;
                     // sort key: direction, then length -- a sub-pass of 8 out-scans then (almost always) runs one way,
                     // which lets the sweep use a compile-time stride (immediate address offsets, 4 steps per pointer bump)
                     const int L = (gate ? (dir > 0 ? S - 1 - d1_in : d1_in) : 0) + 8;
@@ -678,17 +706,16 @@ __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThread
                 float c0 = 0.f, c1 = 0.f, c2 = 0.f, ca = 0.f;
                 bool fast = false;
                 if (T.valid) {
-                    const float4* lci = ci + (size_t)line * Sp;
                     {   // in-scan (rasterize.py:662-730): reference colour = outside pixel, only pixels that show this face
-                        const float4 cout = lci[T.d1_out];
+                        const float4 cout = colour_at(line, T.d1_out);
                         const float ra = (kMode == 3) ? ((__float_as_int(cout.w) >= 0) ? 1.0f : 0.0f) : 0.0f;
                         for (int d1 = T.in_from; d1 <= T.in_to && !NR_SKIP(p, 1); d1++) {
-                            if (__float_as_int(lci[d1].w) != fn) continue;
+                            if (fim_at(line, d1) != fn) continue;
                             visit(T, line, d1, cout.x, cout.y, cout.z, ra, acc0, acc1);
                         }
                     }
                     // out-scan (rasterize.py:604-659): reference colour = inside pixel
-                    const float4 cin = lci[T.d1_in];
+                    const float4 cin = colour_at(line, T.d1_in);
                     c0 = cin.x; c1 = cin.y; c2 = cin.z;
                     ca = (kMode == 3) ? ((__float_as_int(cin.w) >= 0) ? 1.0f : 0.0f) : 0.0f;
                     fast = T.has0 && T.has1;
@@ -989,13 +1016,18 @@ inline float float_le(double d) {
     return f;
 }
 
+template <int kMode, int kT, bool kIdx, bool kCol>
+int launch_edge_scan_c(const BwdParams& p, int nstrips, size_t smem, cudaStream_t stream) {
+    static nr_internal::SmemOptIn optin;
+    if (optin.ensure(k_edge_scan<kMode, kT, kIdx, kCol>, smem) != cudaSuccess) return NR_ERR_CUDA;
+    nr_internal::LaunchScope ls("k_edge_scan", stream);
+    k_edge_scan<kMode, kT, kIdx, kCol><<<dim3(nstrips, 2, p.B), kT, smem, stream>>>(p);
+    return NR_OK;
+}
 template <int kMode, int kT, bool kIdx>
 int launch_edge_scan_i(const BwdParams& p, int nstrips, size_t smem, cudaStream_t stream) {
-    static nr_internal::SmemOptIn optin;
-    if (optin.ensure(k_edge_scan<kMode, kT, kIdx>, smem) != cudaSuccess) return NR_ERR_CUDA;
-    nr_internal::LaunchScope ls("k_edge_scan", stream);
-    k_edge_scan<kMode, kT, kIdx><<<dim3(nstrips, 2, p.B), kT, smem, stream>>>(p);
-    return NR_OK;
+    return p.col_smem ? launch_edge_scan_c<kMode, kT, kIdx, true>(p, nstrips, smem, stream)
+                      : launch_edge_scan_c<kMode, kT, kIdx, false>(p, nstrips, smem, stream);
 }
 template <int kMode, int kT>
 int launch_edge_scan_t(const BwdParams& p, int nstrips, size_t smem, cudaStream_t stream) {
@@ -1024,6 +1056,15 @@ struct BinLayout {
     size_t ncounters, off_cnt, off_off, off_cursor, off_list, total;
 };
 // strip width from the shared-memory budget; workspace = boxes | counters | offsets | cursors | lists
+// Shared-memory bytes per staged pixel: pairs P, Q (16) [+ R (4)] plus either {colours, face index} (16) or, above
+// kColSmemMaxS, the face index alone (4) -- see k_edge_scan.  [raster 512, 70 k faces, batch 32: 3.19 -> see DESIGN.md]
+#ifndef NR_COL_SMEM_MAX_S
+#define NR_COL_SMEM_MAX_S 256
+#endif
+constexpr int kColSmemMaxS = NR_COL_SMEM_MAX_S;
+inline bool strip_keeps_colours(int S) { return S <= kColSmemMaxS; }
+inline int strip_rec_bytes(int S, bool rgb_and_alpha) { return (strip_keeps_colours(S) ? 32 : 20) + (rgb_and_alpha ? 4 : 0); }
+
 BinLayout bin_layout(int B, int F, int S, int rec_bytes) {
     BinLayout L{};
     size_t strip_bytes = kStripBytesDefault;
@@ -1055,7 +1096,7 @@ extern "C" size_t nr_b200_backward_workspace_bytes(int32_t B, int32_t F, int32_t
     (void)ts;
     if (B <= 0 || F <= 0 || S <= 0) return 16;
     const bool both = (flags & NR_RETURN_RGB) && (flags & NR_RETURN_ALPHA);
-    return bin_layout(B, F, S, both ? 36 : 32).total;
+    return bin_layout(B, F, S, strip_rec_bytes(S, both)).total;
 }
 
 extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_stream) {
@@ -1131,8 +1172,9 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
         uint2* bbox = (uint2*)a->workspace;
         uint2* cbox = (uint2*)((char*)a->workspace + nr_align_up((size_t)B * F * sizeof(uint2), 256));
         const bool use_rgb = rgb && p.g_rgb, use_alpha = alpha && p.g_alpha;
-        const int rec_bytes = (use_rgb && use_alpha) ? 36 : 32;
-        const BinLayout L = bin_layout(B, F, S, (rgb && alpha) ? 36 : 32);  // same strip width as the workspace query
+        const int rec_bytes = strip_rec_bytes(S, use_rgb && use_alpha);
+        const BinLayout L = bin_layout(B, F, S, strip_rec_bytes(S, rgb && alpha));  // same strip width as the workspace query
+        p.col_smem = strip_keeps_colours(S) ? 1 : 0;
         const int W = L.W;
         p.W = W; p.w_log2 = L.w_log2; p.nstrips = L.nstrips;
         p.len_shift = 3;
