@@ -44,6 +44,9 @@
 #ifndef NR_ES_UNROLL
 #define NR_ES_UNROLL 2          // steady-state out-scan steps per pointer bump
 #endif
+#ifndef NR_TG_COMBINE
+#define NR_TG_COMBINE 2         // shuffle steps that merge neighbouring lanes' contributions to the same texels (0: off)
+#endif
 #ifndef NR_TG_MIN_CTAS
 #define NR_TG_MIN_CTAS 6
 #endif
@@ -851,15 +854,32 @@ __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThread
 }
 
 // --------------------------------------------------------------------------------------------- k_texture_grad
-__global__ void __launch_bounds__(256, NR_TG_MIN_CTAS) k_texture_grad(const __grid_constant__ BwdParams p) {
+// Neighbouring pixels of a face often blend the SAME eight texels (the same cell of the texture cube: 31 % of the
+// covered pixels at the headline shape, 57 % at raster 512), and the L2 pays per reduction it receives.  Lanes of a warp
+// that sit next to each other with the same (cube, cell) therefore add their 8 x 3 contributions together with
+// kTgCombine shuffle steps first (runs of up to 2^kTgCombine lanes collapse into one lane's reductions).
+template <int kTgCombine>
+__global__ void __launch_bounds__(256, kTgCombine ? 4 : NR_TG_MIN_CTAS) k_texture_grad(const __grid_constant__ BwdParams p) {
     const int S = p.S;
     const size_t plane = (size_t)S * S;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel within the image (image orientation)
     const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
     const int fn = (i < plane) ? __ldg(p.fim + (size_t)b * plane + i) : -1;
     const bool want_light = p.grad_face_light != nullptr;  // uniform
-    if (fn < 0 && !want_light) return;
+    if (kTgCombine) {
+        if (!want_light && !__any_sync(0xffffffffu, fn >= 0)) return;  // warp-uniform
+    } else {
+        if (fn < 0 && !want_light) return;
+    }
     float gl0 = 0.0f, gl1 = 0.0f, gl2 = 0.0f;  // d loss / d face_light of this pixel
+    float val[4][6];                           // contributions to the four corner pairs (6 consecutive floats each)
+    float* tp[4] = {nullptr, nullptr, nullptr, nullptr};
+    long long key = -1 - (long long)lane;      // (cube, cell, orientation): equal keys <=> the same eight texels
+#pragma unroll
+    for (int pr = 0; pr < 4; pr++)
+#pragma unroll
+        for (int k = 0; k < 6; k++) val[pr][k] = 0.0f;
     if (fn >= 0) {
         const int row = (int)(i / S), col = (int)(i % S);
         const bool aa = (p.flags & NR_ANTI_ALIASING) != 0;
@@ -907,15 +927,50 @@ __global__ void __launch_bounds__(256, NR_TG_MIN_CTAS) k_texture_grad(const __gr
             g0 *= __ldg(lp); g1 *= __ldg(lp + 1); g2 *= __ldg(lp + 2);
         }
         float* gt = p.grad_textures + cube_off;
+        key = (((long long)(cube_off / 3) + nr::corner_index(tc, 0, ts)) << 1) | (rev ? 1 : 0);
         // The two corners that differ only along the fastest texture axis (axis 2; axis 0 of a reversed cube) are
-        // neighbours in memory: 6 consecutive floats per corner pair.  They are scattered with the widest vector
-        // reductions their alignment allows (red.global.add.v4/v2.f32, sm_90+): 2-4 requests per pair instead of 6.
+        // neighbours in memory: 6 consecutive floats per corner pair.
 #pragma unroll
         for (int pr = 0; pr < 4; pr++) {
             const int pn_lo = rev ? (pr << 1) : pr, pn_hi = rev ? (pn_lo | 1) : (pn_lo | 4);
             const float w_lo = nr::corner_weight(tc, pn_lo), w_hi = nr::corner_weight(tc, pn_hi);
-            float* t = gt + (rev ? nr::corner_index_rev(tc, pn_lo, ts) : nr::corner_index(tc, pn_lo, ts)) * 3;
-            const float v0 = w_lo * g0, v1 = w_lo * g1, v2 = w_lo * g2, v3 = w_hi * g0, v4 = w_hi * g1, v5 = w_hi * g2;
+            tp[pr] = gt + (rev ? nr::corner_index_rev(tc, pn_lo, ts) : nr::corner_index(tc, pn_lo, ts)) * 3;
+            val[pr][0] = w_lo * g0; val[pr][1] = w_lo * g1; val[pr][2] = w_lo * g2;
+            val[pr][3] = w_hi * g0; val[pr][4] = w_hi * g1; val[pr][5] = w_hi * g2;
+        }
+    }
+    bool issue = fn >= 0;
+    if (kTgCombine) {
+        // runs of neighbouring lanes with the same key: after k steps lane l holds the sum over lanes l .. l + 2^k - 1 of
+        // its run; every 2^kTgCombine-th lane of a run issues
+        const long long key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || key != key_prev);
+        const uint32_t later = heads & ~((2u << lane) - 1u);
+        const int run_end = (lane == 31 || later == 0) ? 31 : (__ffs(later) - 2);
+        const int run_start = 31 - __clz(heads & ((2u << lane) - 1u));
+        if (heads != 0xffffffffu) {  // warp-uniform: somebody has a neighbour to merge with
+#pragma unroll
+            for (int step = 0; step < kTgCombine; step++) {
+                const int off = 1 << step;
+                const bool take = lane + off <= run_end;
+#pragma unroll
+                for (int pr = 0; pr < 4; pr++)
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        const float t = __shfl_down_sync(0xffffffffu, val[pr][k], off);
+                        if (take) val[pr][k] += t;
+                    }
+            }
+            issue = issue && (((lane - run_start) & ((1 << kTgCombine) - 1)) == 0);
+        }
+    }
+    if (issue) {
+        // scattered with the widest vector reductions the alignment allows (red.global.add.v4/v2.f32, sm_90+): 2-4
+        // requests per pair instead of 6
+#pragma unroll
+        for (int pr = 0; pr < 4; pr++) {
+            float* t = tp[pr];
+            const float v0 = val[pr][0], v1 = val[pr][1], v2 = val[pr][2], v3 = val[pr][3], v4 = val[pr][4], v5 = val[pr][5];
             switch ((reinterpret_cast<uintptr_t>(t) >> 2) & 3) {
                 case 0: red_add_v4(t, v0, v1, v2, v3); red_add_v2(t + 4, v4, v5); break;
                 case 2: red_add_v2(t, v0, v1); red_add_v4(t + 2, v2, v3, v4, v5); break;
@@ -928,7 +983,6 @@ __global__ void __launch_bounds__(256, NR_TG_MIN_CTAS) k_texture_grad(const __gr
     }
     if (!want_light) return;
     // warp-aggregated scatter of the light gradient: runs of neighbouring lanes that show the same face
-    const int lane = threadIdx.x & 31;
     const int fn_prev = __shfl_up_sync(0xffffffffu, fn, 1);
     const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || fn != fn_prev);
     const uint32_t later = heads & ~((2u << lane) - 1u);
@@ -1162,7 +1216,7 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
     const dim3 pgrid((unsigned)(((size_t)S * S + 255) / 256), B);
     if (part_tex && rgb && p.g_rgb) {
         nr_internal::LaunchScope ls("k_texture_grad", stream);
-        k_texture_grad<<<pgrid, 256, 0, stream>>>(p);
+        k_texture_grad<NR_TG_COMBINE><<<pgrid, 256, 0, stream>>>(p);
     }
     if (!part_faces) return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
 
