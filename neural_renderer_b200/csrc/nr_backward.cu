@@ -44,6 +44,17 @@
 #ifndef NR_ES_UNROLL
 #define NR_ES_UNROLL 2          // steady-state out-scan steps per pointer bump
 #endif
+#ifndef NR_FILL_AT_END
+#define NR_FILL_AT_END 0        // where an edge-scan CTA does its share of the grad_textures zero-fill: 0 = first, 1 = last
+#endif
+#ifndef NR_FILL_STREAMING
+#define NR_FILL_STREAMING 1
+#endif
+#if NR_FILL_STREAMING
+#define NR_FILL_STORE(ptr, v) __stcs(ptr, v)
+#else
+#define NR_FILL_STORE(ptr, v) (*(ptr) = (v))
+#endif
 #ifndef NR_TG_COMBINE
 #define NR_TG_COMBINE 2         // shuffle steps that merge neighbouring lanes' contributions to the same texels (0: off)
 #endif
@@ -92,6 +103,9 @@ struct BwdParams {
     int len_shift;  // scan length >> len_shift -> one of 32 sort buckets
     int stage_fast; // even raster + 8-byte aligned maps: strips are staged with 8-byte loads
     int col_smem;   // the strip keeps the pixels' colours in shared memory (rasters up to kColSmemMaxS)
+    float* zero_dst;          // 16-byte aligned buffer that the edge scan's CTAs zero-fill on the side (grad_textures), or nullptr
+    unsigned long long zero_count;    // floats
+    unsigned long long zero_per_cta;  // float4 per CTA
 #ifdef NR_B200_DEBUG_KNOBS
     int debug_skip; // ablation knob of experiment builds (NR_B200_ES_SKIP): 1 = no in-scan, 2 = no out-scan, 4 = no task processing
 #endif
@@ -337,6 +351,21 @@ __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThread
     const int tid = threadIdx.x, lane = tid & 31;
     const int axis = blockIdx.y, b = blockIdx.z;
     const int l0 = blockIdx.x * W;
+    // Side job: the zero-fill of grad_textures (246 MB of pure HBM writes at the headline shape, 44 us as a memset of its
+    // own) is spread over this kernel's CTAs -- the edge scan leaves the DRAM at 3 %, so the (streaming) stores ride
+    // along; K6 runs after this kernel instead of before it.
+    auto side_fill = [&]() {
+        if (!p.zero_dst) return;
+        const unsigned long long cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
+        const unsigned long long n4 = p.zero_count >> 2;
+        const unsigned long long lo = cta * p.zero_per_cta, hi = min(lo + p.zero_per_cta, n4);
+        float4* d = reinterpret_cast<float4*>(p.zero_dst);
+        for (unsigned long long i = lo + tid; i < hi; i += kThreads) NR_FILL_STORE(d + i, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        if (cta == 0 && tid < (int)(p.zero_count & 3)) p.zero_dst[(n4 << 2) + tid] = 0.0f;
+    };
+#if NR_FILL_AT_END == 0
+    side_fill();
+#endif
     const int nlines = min(W, S - l0);
     const bool aa = (p.flags & NR_ANTI_ALIASING) != 0;
     const size_t plane = (size_t)S * S;
@@ -851,6 +880,9 @@ __global__ void __launch_bounds__(kThreads, NR_ES_CTAS_PER_1024 * 1024 / kThread
         nface = 0;
         __syncthreads();
     }
+#if NR_FILL_AT_END == 1
+    side_fill();
+#endif
 }
 
 // --------------------------------------------------------------------------------------------- k_texture_grad
@@ -1183,6 +1215,16 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
 
     const size_t ncubes = (flags & NR_TEX_FILL_BACK) ? (size_t)F / 2 : (size_t)F;
     const size_t tex_items = (flags & NR_TEX_SHARED) ? 1 : (size_t)B;
+    const size_t tex_floats = tex_items * ncubes * ts * ts * ts * 3;
+    // When one call runs both halves, grad_textures is zero-filled by the CTAs of the edge scan (a side job of an
+    // issue-bound kernel instead of 44 us of memset) and K6 runs after the edge scan.  Separate halves (the caller wants
+    // the texture gradient first, for a collective) and unaligned buffers keep the memset.
+    const bool scan_will_run = part_faces && ((rgb && a->grad_rgb) || (alpha && a->grad_alpha));
+    bool fill_in_scan = !(flags & NR_GRAD_ACCUMULATE) && part_tex && part_faces && rgb && a->grad_rgb && scan_will_run &&
+                        (((uintptr_t)a->grad_textures & 15) == 0);
+#ifdef NR_NO_FILL_IN_SCAN
+    fill_in_scan = false;
+#endif
     if (!(flags & NR_GRAD_ACCUMULATE)) {
         nr_internal::prof_begin("memset_grads", stream);
         if (part_faces) {
@@ -1191,7 +1233,7 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
                 : cudaMemsetAsync(a->grad_faces, 0, (size_t)B * F * 9 * sizeof(float), stream);
             if (e != cudaSuccess) return NR_ERR_CUDA;
         }
-        if (part_tex && rgb && cudaMemsetAsync(a->grad_textures, 0, tex_items * ncubes * ts * ts * ts * 3 * sizeof(float), stream) != cudaSuccess)
+        if (part_tex && rgb && !fill_in_scan && cudaMemsetAsync(a->grad_textures, 0, tex_floats * sizeof(float), stream) != cudaSuccess)
             return NR_ERR_CUDA;
         if (part_tex && rgb && a->grad_face_light && cudaMemsetAsync(a->grad_face_light, 0, (size_t)B * F * 3 * sizeof(float), stream) != cudaSuccess)
             return NR_ERR_CUDA;
@@ -1214,10 +1256,12 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
     p.tex_val = (float)tmax;
 
     const dim3 pgrid((unsigned)(((size_t)S * S + 255) / 256), B);
-    if (part_tex && rgb && p.g_rgb) {
+    auto launch_texture_grad = [&]() {
         nr_internal::LaunchScope ls("k_texture_grad", stream);
         k_texture_grad<NR_TG_COMBINE><<<pgrid, 256, 0, stream>>>(p);
-    }
+    };
+    // K6 first, unless its output buffer is zero-filled by the edge scan
+    if (part_tex && rgb && p.g_rgb && !fill_in_scan) launch_texture_grad();
     if (!part_faces) return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
 
     // K5 runs when an rgb or alpha gradient exists (rasterize.py:523); without upstream gradients it contributes 0
@@ -1288,11 +1332,17 @@ extern "C" int nr_b200_backward(const nr_b200_backward_args* a, void* cuda_strea
         }
         p.bbox = bbox;
         p.strip_cnt = cnt; p.strip_off = off; p.strip_list = list;
+        if (fill_in_scan) {
+            const unsigned long long ncta = (unsigned long long)nstrips * 2 * B, n4 = tex_floats >> 2;
+            p.zero_dst = a->grad_textures; p.zero_count = tex_floats; p.zero_per_cta = (n4 + ncta - 1) / ncta;
+        }
         int rc;
         if (use_rgb && use_alpha) rc = launch_edge_scan<3>(p, nstrips, smem, stream);
         else if (use_rgb) rc = launch_edge_scan<1>(p, nstrips, smem, stream);
         else rc = launch_edge_scan<2>(p, nstrips, smem, stream);
         if (rc != NR_OK) return rc;
+        p.zero_dst = nullptr;
+        if (fill_in_scan) launch_texture_grad();
     }
     if (depth && p.g_depth) {
         nr_internal::LaunchScope ls("k_depth_grad", stream);
