@@ -2,9 +2,11 @@
 //
 // Replaces Rasterize.backward_gpu (reference neural_renderer/rasterize.py:849-889):
 //
-//   k_strip_bin /     pre-pass of K5: every front face is appended to the list of each W-line strip (per axis) that
-//   k_strip_scan      its pixel box overlaps -- count, exclusive scan per (item, axis), fill; counted per CTA in shared
-//                     memory first.  Faces spanning more than kWideStrips strips go to one "wide" list per item / axis.
+//   k_strip_bin       pre-pass of K5, two launches (count, fill): every front face is appended to the list of each W-line
+//                     strip (per axis) that its pixel box overlaps.  The counting pass computes the boxes and counts per
+//                     CTA in shared memory first; every CTA of the fill pass scans its item's counters itself.  Faces
+//                     spanning more than kWideStrips strips go to one "wide" list per item / axis.  (Rasters with more
+//                     than 2048 strips per axis use k_face_bbox + k_strip_bin_global + k_strip_scan instead.)
 //   k_edge_scan       K5, the approximate-gradient image scan (rasterize.py:528-748).  The reference runs one thread
 //                     per face that walks image columns / rows straight out of global memory.  Here a CTA owns a strip
 //                     of W image lines (columns for axis 0, rows for axis 1) of one batch item and stages it once in
@@ -16,11 +18,13 @@
 //                     reproduces the reference's discrete decisions exactly (crossing pixel floor/ceil, the
 //                     `face_index_map == fn` gates, the in-scan limit) and accumulates the same
 //                     -relu(dI . dL/dI) / dist terms; only the summation order differs (fp32 atomics into grad_faces).
+//                     Its CTAs also zero-fill grad_textures on the side when one call runs both halves of the pass.
 //   k_texture_grad    K6 (rasterize.py:760-792): the 8 trilinear weights/indices are recomputed from the saved
 //                     weight/depth maps with the forward expression tree instead of being stored (64 B/pixel in the
 //                     reference) and scattered with vector float reductions (red.global.add.v2/v4.f32); applies the
 //                     per-face light factor / fill_back cube sharing of the forward sampler and reduces d loss /
-//                     d face_light per run of lanes.
+//                     d face_light per run of lanes; neighbouring lanes that blend the same eight texels merge their
+//                     contributions with shuffles before the reductions.
 //   k_depth_grad      K7 (rasterize.py:805-847): analytic d zp / d(x, y, z) of the winning face, summed per run of
 //                     neighbouring lanes that show the same face before the atomics.
 //
