@@ -97,12 +97,12 @@ def kernel_bytes(B, F, S, ts):
         "memset_zbuf": 8 * P,
         "k_raster_faces": 36 * B * F + 8 * P,
         "k_resolve": 8 * P + 12 * T * B * F + 32 * P,
-        # zero-fill of grad_faces + grad_textures
-        "memset_grads": 36 * B * F + 12 * T * B * F,
+        # zero-fill of grad_faces (the zero-fill of grad_textures is a side job of k_edge_scan's CTAs, below)
+        "memset_grads": 36 * B * F,
         # K6: grad_rgb 12 + fim 4 + weight_map 12 + depth_map 4 per pixel in, grad_textures out (reductions)
         "k_texture_grad": 32 * P + 12 * T * B * F,
-        # K5: faces in, grad_faces out, rgb 12 + grad_rgb 12 + fim 4 per pixel in
-        "k_edge_scan": 72 * B * F + 28 * P,
+        # K5: faces in, grad_faces out, rgb 12 + grad_rgb 12 + fim 4 per pixel in; plus grad_textures zero-filled once
+        "k_edge_scan": 72 * B * F + 28 * P + 12 * T * B * F,
         # strip binning, two launches: (count) faces in, boxes out; (fill) boxes in, lists out (<= 8 entries per face and
         # axis; sparse) -- per launch: the average of the two
         "k_strip_bin": (36 * B * F + 8 * B * F + 8 * B * F) // 2,
@@ -763,7 +763,7 @@ def main():
         out["roofline_fwd"] = dict(roof(fwd_bytes, fwd_ms), kernels=" + ".join(fwd_names),
                                    note="forward rasterize pass, 391.5 MB algorithmic (SURVEY.md 8(d))")
         out["roofline_bwd"] = dict(roof(bwd_bytes, bwd_ms),
-                                   kernels="memset_grads + k_texture_grad + k_strip_bin x2 + k_edge_scan",
+                                   kernels="memset_grads + k_strip_bin x2 + k_edge_scan (+ zero-fill of grad_textures) + k_texture_grad",
                                    note="whole backward pass, 436.6 MB algorithmic (SURVEY.md 8(d))")
         out["roofline_step"] = roof(fwd_bytes + bwd_bytes, ms / args.steps)
         # issue-slot roofline of the kernels the HBM roof does not describe (warp instructions from the ncu capture)
