@@ -573,11 +573,13 @@ __global__ void __launch_bounds__(256, kAA ? 5 : NR_RESOLVE_MIN_CTAS) k_resolve(
         if (col >= S || row >= S) return;
         const Shaded s = shade_pixel<kLit>(p, b, __ldg(zb + (uint32_t)yi * S + col), col, yi, bgr, bgg, bgb);
         const uint32_t o = (uint32_t)row * S + col;
-        fim[o] = s.fim;
-        dmap[o] = s.depth;
-        wmap[o] = s.w0; wmap[o + plane] = s.w1; wmap[o + 2 * plane] = s.w2;
-        if (alpha) alpha[o] = s.alpha;
-        if (want_rgb) { rgb[o] = s.r; rgb[o + plane] = s.g; rgb[o + 2 * plane] = s.b; }
+        // streaming stores: 134 MB of maps that nothing reads again before the backward pass should not push the
+        // z-buffer, the face records and the texture cubes out of the L2 [k_resolve 75.3 -> 72.0 us]
+        __stcs(fim + o, s.fim);
+        __stcs(dmap + o, s.depth);
+        __stcs(wmap + o, s.w0); __stcs(wmap + o + plane, s.w1); __stcs(wmap + o + 2 * plane, s.w2);
+        if (alpha) __stcs(alpha + o, s.alpha);
+        if (want_rgb) { __stcs(rgb + o, s.r); __stcs(rgb + o + plane, s.g); __stcs(rgb + o + 2 * plane, s.b); }
     } else {
         // thread = one pooled API pixel = one 2x2 quad of the raster
         const int H = S >> 1;
@@ -593,11 +595,11 @@ __global__ void __launch_bounds__(256, kAA ? 5 : NR_RESOLVE_MIN_CTAS) k_resolve(
             const int yi = S - 1 - row;
             const Shaded s = shade_pixel<kLit>(p, b, __ldg(zb + (uint32_t)yi * S + xi), xi, yi, bgr, bgg, bgb);
             const uint32_t o = (uint32_t)row * S + xi;
-            fim[o] = s.fim;
-            dmap[o] = s.depth;
-            wmap[o] = s.w0; wmap[o + plane] = s.w1; wmap[o + 2 * plane] = s.w2;
-            if (alpha) alpha[o] = s.alpha;
-            if (want_rgb) { rgb[o] = s.r; rgb[o + plane] = s.g; rgb[o + 2 * plane] = s.b; }
+            __stcs(fim + o, s.fim);
+            __stcs(dmap + o, s.depth);
+            __stcs(wmap + o, s.w0); __stcs(wmap + o + plane, s.w1); __stcs(wmap + o + 2 * plane, s.w2);
+            if (alpha) __stcs(alpha + o, s.alpha);
+            if (want_rgb) { __stcs(rgb + o, s.r); __stcs(rgb + o + plane, s.g); __stcs(rgb + o + 2 * plane, s.b); }
             sr += s.r; sg += s.g; sb += s.b; sa += s.alpha; sd += s.depth;
         }
         const uint32_t oo = (uint32_t)orow * H + col;
