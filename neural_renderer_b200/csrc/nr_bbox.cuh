@@ -1,10 +1,12 @@
 // nr_bbox.cuh -- per-face screen bounding boxes shared by the forward and backward passes.
 //
-// k_face_bbox: one thread per face.  Back faces (rasterize.py:252/:306/:540) and faces with a non-finite x/y (they
-// can never win a pixel: their barycentric weights clamp to 0 and zp becomes NaN) get an empty box; every other
-// face gets a conservative pixel box (8 bytes) that contains every pixel centre the reference's edge tests can
-// accept and every column/row its edge scan can start from.  One union box per group of 32 consecutive faces (a warp
-// of this kernel) lets the forward tiles skip whole groups.  This is the only per-face scratch either pass needs.
+// face_pixel_box: back faces (rasterize.py:252/:306/:540) and faces with a non-finite x/y (they can never win a pixel:
+// their barycentric weights clamp to 0 and zp becomes NaN) get no box; every other face gets a conservative pixel box
+// that contains every pixel centre the reference's edge tests can accept (forward: <true>, with the thin-face margin)
+// or every column / row its edge scan can start from (backward: <false>).  The forward evaluates it per face inside
+// k_raster_faces, the backward inside the counting pass of k_strip_bin (8 bytes per face in the workspace).
+// k_face_bbox is the stand-alone kernel of the same box, used only by the global-atomics binning path of rasters with
+// more than 2048 strips per axis.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
